@@ -1,0 +1,253 @@
+/*
+ * rtb.h -- C ABI of librtb.so, the B200 (sm_100a) batch ray tracer behind the `raytrace.raytrace` Python API.
+ *
+ * The reference (QI2lab/ray_trace_pb) has no FFI of its own: its boundary is the Python call
+ *     System.ray_trace(rays, initial_material, final_material)            src/raytrace/raytrace.py:641-661
+ * which loops `surface.propagate(...)` (raytrace.py:1160-1234, 1238-1303, 1601-1801) over whole NumPy arrays.
+ * Every entry point below replaces one such Python-level operator; the reference lines it stands in for are cited
+ * next to it.  Bindings: plain pointers and sizes only, no torch / numpy types.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - A ray is 8 contiguous doubles (x, y, z, dx, dy, dz, phase[rad], wavelength[um])      raytrace.py:1-5
+ *   - Ray batches are row-major (N, 8); histories are (n_slabs, N, 8).
+ *   - Slab index j of a trace through S surfaces: 0 = launch rays, 2k+1 = at surface k, 2k+2 = just after surface k.
+ *   - Numerical invalidity is in-band NaN, never an error code (raytrace.py:303-304, 1192, 1221, 1226, 1760).
+ *   - Return value: 0 on success; negative rtb_status for structural problems (mapped to ValueError /
+ *     NotImplementedError / RuntimeError by the Python host).  rtb_last_error() gives the text (thread local).
+ *   - "dev" pointers are CUDA device pointers on the given device; "host" pointers are ordinary host memory.
+ *   - The caller owns every buffer.  The library never frees or writes its inputs.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry points only enqueue
+ *     work; host entry points return after the results are in the host buffers.
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef RTB_H
+#define RTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_ABI_VERSION 1
+#define RTB_MAX_SURFACES 64
+#define RTB_MAX_WAVELENGTHS 16 /* rows of the host refractive-index table (one extra row answers NaN wavelengths) */
+#define RTB_MAX_KEEP (2 * RTB_MAX_SURFACES + 1)
+
+typedef enum rtb_status {
+    RTB_OK = 0,
+    RTB_ERR_INVALID = -1,     /* structurally invalid argument (-> ValueError)              */
+    RTB_ERR_UNSUPPORTED = -2, /* valid but not implemented on the device (-> NotImplementedError) */
+    RTB_ERR_CUDA = -3,        /* CUDA runtime failure (-> RuntimeError)                     */
+    RTB_ERR_NOMEM = -4
+} rtb_status;
+
+/* raytrace.py:1306 FlatSurface, :1435 SphericalSurface, :1377 PlaneMirror, :1558 PerfectLens */
+typedef enum rtb_surface_kind {
+    RTB_SURF_FLAT = 0,
+    RTB_SURF_SPHERE = 1,
+    RTB_SURF_MIRROR = 2,
+    RTB_SURF_PERFECT_LENS = 3
+} rtb_surface_kind;
+
+/* materials.py:59 Constant, :6 Material (Sellmeier), anything else = host table only */
+typedef enum rtb_material_kind {
+    RTB_MAT_CONSTANT = 0,
+    RTB_MAT_SELLMEIER = 1,
+    RTB_MAT_TABLE_ONLY = 2
+} rtb_material_kind;
+
+/*
+ * One optical surface.  All derived scalars are computed on the host by the same Python expressions the
+ * reference uses, so that the device arithmetic starts from bit-identical constants:
+ *   radius_sq = radius**2, abs_radius = abs(radius)                  raytrace.py:1499, 1528
+ *   normal_f  = normal * focal_len                                   raytrace.py:1683
+ *   sin_alpha = np.sin(alpha)                                        raytrace.py:1758
+ * `normal` is the geometric plane normal (flat / mirror / perfect lens; raytrace.py:1320, 1389, 1576), `input_axis`
+ * the axis used by the "ray comes from the front" cull and the sphere's aperture test (raytrace.py:1189, 1531).
+ * System.reverse() flips only the latter (raytrace.py:409-411), so both are carried.
+ */
+typedef struct rtb_surface {
+    int32_t kind; /* rtb_surface_kind */
+    int32_t reserved;
+    double center[3];
+    double normal[3];
+    double input_axis[3];
+    double radius;
+    double radius_sq;
+    double abs_radius;
+    double aperture_rad;
+    double focal_len;
+    double normal_f[3];
+    double sin_alpha;
+} rtb_surface;
+
+/* Sellmeier: n = sqrt(((b0 w^2/(w^2-c0) + b1 w^2/(w^2-c1)) + b2 w^2/(w^2-c2)) + 1)      materials.py:39-51 */
+typedef struct rtb_material {
+    int32_t kind; /* rtb_material_kind */
+    int32_t reserved;
+    double b[3];
+    double c[3];
+    double n_const;
+} rtb_material;
+
+/*
+ * A sequential system: S surfaces and the S+1 media around them, i.e. the list
+ * [initial_material] + system.materials + [final_material] of raytrace.py:653.
+ *
+ * Refractive indices come from one of two places:
+ *   n_wavelengths > 0 : `wavelengths[n_wavelengths]` lists every distinct wavelength bit pattern of the batch and
+ *        `n_table[(n_wavelengths + 1) * (S + 1)]` (row-major, row = wavelength, column = medium) holds material.n()
+ *        evaluated on the host by the user's own Python objects; the extra last row is the answer for a NaN (or
+ *        unlisted) wavelength.  Works for every material kind, bit exact by construction.
+ *   n_wavelengths == 0: the kernel evaluates Constant / Sellmeier media per ray; RTB_MAT_TABLE_ONLY media are
+ *        then refused with RTB_ERR_UNSUPPORTED.
+ */
+typedef struct rtb_system {
+    int32_t n_surfaces;
+    int32_t n_wavelengths;
+    const rtb_surface *surfaces;   /* host, n_surfaces */
+    const rtb_material *materials; /* host, n_surfaces + 1 */
+    const double *wavelengths;     /* host, n_wavelengths (may be NULL when 0) */
+    const double *n_table;         /* host, (n_wavelengths + 1) * (n_surfaces + 1) (may be NULL when 0) */
+} rtb_system;
+
+typedef enum rtb_precision {
+    RTB_F64_EXACT = 0, /* reference operation order, no FMA contraction: bit-identical to the NumPy path */
+    RTB_F32_FAST = 1   /* fp32 geometry, fp64 phase accumulation; tolerance stated in DESIGN.md          */
+} rtb_precision;
+
+typedef enum rtb_keep_mode {
+    RTB_KEEP_ALL = 0,  /* out = (2S+1, N, 8): what System.ray_trace returns (raytrace.py:1229-1232)   */
+    RTB_KEEP_LAST = 1, /* out = (1, N, 8): slab 2S only                                               */
+    RTB_KEEP_LIST = 2, /* out = (n_keep, N, 8): slabs keep_slabs[0..n_keep), strictly increasing      */
+    RTB_KEEP_NONE = 3  /* no ray output (reductions only)                                             */
+} rtb_keep_mode;
+
+/*
+ * Optional fused reductions evaluated at one slab of the trace (the "ray fan -> pupil phase -> PSF accumulation"
+ * and the spot statistics of BASELINE.json).  Coordinates are taken in a plane basis:
+ *     u = (p - origin) . e1,   v = (p - origin) . e2
+ * A ray contributes when u, v and phase are all finite (not NaN).
+ *
+ *   stats_dev  (RTB_N_STATS doubles, accumulated with atomics -- zero it first):
+ *       [0] count  [1] sum u  [2] sum v  [3] sum u^2  [4] sum v^2  [5] sum u v
+ *       [6] sum (phase - phase_ref)  [7] sum (phase - phase_ref)^2  [8] min u [9] max u [10] min v [11] max v
+ *       (min/max slots must be initialised to +inf / -inf by the caller; rtb_reduce_init does all of this)
+ *   grid_dev   (3 * grid_n * grid_n doubles, accumulated with atomics):
+ *       plane 0: sum cos(phase - phase_ref), plane 1: sum sin(phase - phase_ref), plane 2: count,
+ *       cell (iu, iv) at [plane * G*G + iv * G + iu], iu = floor((u + grid_half_width) / cell), cell = 2*half/G;
+ *       rays outside [-half, half) are counted in stats only.
+ */
+#define RTB_N_STATS 12
+typedef struct rtb_reduce {
+    int32_t slab;   /* slab index in [0, 2S] at which (p, phase) are sampled */
+    int32_t grid_n; /* G, 0 = no grid */
+    double origin[3];
+    double e1[3];
+    double e2[3];
+    double phase_ref;
+    double grid_half_width;
+    double *stats_dev; /* device, RTB_N_STATS, or NULL */
+    double *grid_dev;  /* device, 3*G*G, or NULL       */
+} rtb_reduce;
+
+typedef struct rtb_trace_opts {
+    int32_t precision; /* rtb_precision */
+    int32_t keep_mode; /* rtb_keep_mode */
+    int32_t n_keep;
+    int32_t reserved;
+    const int32_t *keep_slabs; /* host, n_keep entries, for RTB_KEEP_LIST */
+    const rtb_reduce *reduce;  /* host, optional */
+} rtb_trace_opts;
+
+/* On-device ray sources, so that 1e8..1e9-ray batches never exist on the host. */
+typedef enum rtb_source_kind {
+    RTB_SRC_COLLIMATED = 0, /* get_collimated_rays, raytrace.py:99-161:  index = i_disp * n_b + i_phi      */
+    RTB_SRC_FAN = 1,        /* get_ray_fan,         raytrace.py:45-96 :  index = i_phi  * n_a + i_theta    */
+    RTB_SRC_GRID = 2        /* Cartesian grid of parallel rays: index = i_v * n_a + i_u (this library's own) */
+} rtb_source_kind;
+
+/*
+ * kind COLLIMATED: a = displacement (n_a values, linspace(-a_max, a_max, n_a)), b = azimuth (n_b values,
+ *                  arange(n_b)*2pi/n_b + b_start); position = pt + e1*(a cos b) + e2*(a sin b), direction = axis.
+ * kind FAN:        a = polar angle theta (linspace(-a_max, a_max, n_a)), b = azimuth phi (arange(n_b)*2pi/n_b);
+ *                  position = pt, direction = axis cos(theta) + e1 cos(phi) sin(theta) + e2 sin(phi) sin(theta).
+ * kind GRID:       u = linspace(-a_max, a_max, n_a), v = linspace(-b_max, b_max, n_b);
+ *                  position = (pt + e1*u) + e2*v, direction = axis.
+ * e1, e2 are the transverse unit vectors, computed on the host exactly as the reference does (raytrace.py:79-81,
+ * 135-144).  phase = 0, wavelength = `wavelength` for every ray.
+ */
+typedef struct rtb_source {
+    int32_t kind;
+    int32_t reserved;
+    int64_t n_a;
+    int64_t n_b;
+    double a_max;
+    double b_max;   /* GRID only */
+    double b_start; /* COLLIMATED: phi_start */
+    double pt[3];
+    double axis[3];
+    double e1[3];
+    double e2[3];
+    double wavelength;
+} rtb_source;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int rtb_abi_version(void);
+const char *rtb_last_error(void);
+/* number of CUDA devices visible (0 if none); negative rtb_status if the runtime cannot be initialised */
+int rtb_device_count(void);
+/* kernels launched by this library in this process so far (for bench.py's gpu_launches claim) */
+int64_t rtb_launch_count(void);
+
+/* ---- the hot path: replaces System.ray_trace, raytrace.py:641-661 --------------------------------------- */
+/*
+ * rays_in_dev : (N, 8) device.  out_dev : (n_out_slabs, N, 8) device, n_out_slabs per opts->keep_mode
+ * (may be NULL for RTB_KEEP_NONE).  In RTB_KEEP_ALL / RTB_KEEP_LIST slab 0 is a copy of the input rows.
+ * Enqueues on `stream` and returns; no host synchronisation.
+ */
+int rtb_trace_device(const rtb_system *sys, const double *rays_in_dev, int64_t n_rays, double *out_dev,
+                     const rtb_trace_opts *opts, int device, void *stream);
+
+/*
+ * Same trace with HOST buffers (the drop-in call): rays_in_host (N, 8), out_host (n_out_slabs, N, 8).
+ * The library stages chunks through pinned memory on its own streams (copy-in, kernel, copy-out overlapped) and
+ * returns when out_host is complete.  opts->reduce buffers, if given, stay device pointers.
+ */
+int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_rays, double *out_host,
+                   const rtb_trace_opts *opts, int device);
+
+/*
+ * Trace rays produced on the device by `src` (ray indices [first_ray, first_ray + n_rays) of the source's index
+ * space), fused as the prologue of the trace kernel: no input bytes.  out_dev as for rtb_trace_device.
+ */
+int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first_ray, int64_t n_rays,
+                     double *out_dev, const rtb_trace_opts *opts, int device, void *stream);
+
+/* ---- ray sources: replace get_collimated_rays / get_ray_fan, raytrace.py:45-161 --------------------------- */
+int rtb_generate_device(const rtb_source *src, int64_t first_ray, int64_t n_rays, double *rays_out_dev,
+                        int device, void *stream);
+
+/* ---- reductions ------------------------------------------------------------------------------------------- */
+/* zero / initialise the stats vector and grid referenced by `red` (count=0, min=+inf, max=-inf) */
+int rtb_reduce_init(const rtb_reduce *red, int device, void *stream);
+
+/* ---- after the trace: replaces intersect_rays, raytrace.py:164-238 ----------------------------------------- */
+/* ray1_dev, ray2_dev : (N, 8) device; pts_out_dev : (N, 3) device. n1 or n2 may be 1 (broadcast). */
+int rtb_intersect_rays_device(const double *ray1_dev, int64_t n1, const double *ray2_dev, int64_t n2,
+                              double *pts_out_dev, int device, void *stream);
+
+/* ---- measurement helpers ------------------------------------------------------------------------------------ */
+/*
+ * Register-only dependent-chain DFMA micro-benchmark: the FP64-pipe roofline denominator.
+ * Returns warp-level... no: thread-level DFMA instructions per second on `device` in *dfma_per_s.
+ */
+int rtb_measure_dfma_rate(int device, double *dfma_per_s, double *elapsed_ms);
+/* device-to-device copy bandwidth (read+write bytes / s) over `bytes` bytes, for cross-checking MEASURED_PEAKS */
+int rtb_measure_copy_bandwidth(int device, int64_t bytes, double *bytes_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */
