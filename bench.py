@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline measurement: fp64 ray*surfaces/s of the fused trace on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # the reference algorithm on the host cores
+
+Workload (BASELINE.json config 5 / north star): the 10-surface achromat relay of
+scripts/2022_08_24_relay_astigmatism.py (8 spherical + 2 flat surfaces, 6 Sellmeier + 3 constant media, 0.785 um),
+a Cartesian bundle of collimated rays sharded by contiguous index range over the ranks (weak scaling:
+--rays-per-gpu rays on every GPU, 1.25e8 by default = 1e9 rays on 8 GPUs).
+
+One step = one pass of the hot path over this rank's rays, resident in HBM as the reference's (N, 8) float64 array:
+read 64 B/ray, trace 10 surfaces in registers, write the final (N, 8) slab, and -- fused in the same kernel -- the
+spot statistics and the 2048^2 pupil-grid accumulation (sum cos phi, sum sin phi, count); at N > 1 the grid and the
+statistics are all-reduced over NCCL (the only communication).  Timed with CUDA events on the launching stream,
+barrier + synchronize on both sides, max over ranks.
+
+`value` is device-resident throughput; `e2e` is the same trace through the host-buffer C-ABI call
+(rtb_trace_host: pinned host rays in, final slab out, copies inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+# algorithmic FP64-pipe instructions and bytes for the 10-surface relay
+I_ALG_PER_RAY = 2900.0      # 1268 add/mul + 8*(130 div + 74 sqrt)
+F_ALG_PER_RAY = 1472.0      # plain flop count (div = sqrt = 1)
+N_SURFACES = 10
+BYTES_PER_RAY = 128.0       # 64 B in + 64 B out (final-slab mode)
+WAVELENGTH = 0.785
+GRID_N = 2048
+
+
+def relay_system():
+    import systems
+    import ray_trace_pb_b200.materials as rtm
+    import ray_trace_pb_b200.raytrace as rt
+    system = systems.relay10_system(rt, rtm)
+    materials = [rtm.Vacuum()] + list(system.materials) + [rtm.Vacuum()]
+    return system, materials
+
+
+def beam_source(n_rays_total: int):
+    """The whole job's bundle: an on-axis Cartesian grid of collimated rays, half-width 12 mm; ranks take
+    contiguous index ranges of it (ray_trace_pb_b200.sharding.shard_range)."""
+    from ray_trace_pb_b200.device import RaySource
+    side = int(np.ceil(np.sqrt(n_rays_total)))
+    return RaySource.grid([0, 0, 0], 12.0, side, WAVELENGTH, n_v=side), side
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_run(n_threads: int, target_seconds: float = 12.0):
+    """The oracle port (oracle/rt_oracle.c, OpenMP) on a bounded sample of the same workload, all host cores."""
+    import systems
+    import ray_trace_pb_b200.materials as rtm
+    import ray_trace_pb_b200.raytrace as rt
+    from oracle import oracle
+    system = systems.relay10_system(rt, rtm)
+    materials = [rtm.Vacuum()] + list(system.materials) + [rtm.Vacuum()]
+
+    def run(n_side):
+        rays = systems.lattice_rays(n_side, 12.0, 0.0, WAVELENGTH)
+        go = oracle.prepared_trace(system.surfaces, materials, rays, keep_all=False, n_threads=n_threads)
+        t0 = time.perf_counter()
+        go()
+        return rays.shape[0], time.perf_counter() - t0
+
+    n, dt = run(512)                                           # calibration: 262,144 rays
+    rate = n * N_SURFACES / dt
+    side = int(min(4096, max(512, np.sqrt(rate * target_seconds / N_SURFACES))))
+    best = None
+    for _ in range(2):
+        n, dt = run(side)
+        r = n * N_SURFACES / dt
+        best = r if best is None else max(best, r)
+    return best, f"{side}x{side} = {side * side} rays x {N_SURFACES} surfaces, final slab only, best of 2"
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the reference is pure Python and
+    cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import systems
+    import ray_trace_pb_b200.materials as rtm
+    import ray_trace_pb_b200.raytrace as rt
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    system = systems.relay10_system(rt, rtm)
+    materials = [rtm.Vacuum()] + list(system.materials) + [rtm.Vacuum()]
+    side = 2048                                                 # 4.2M rays per step: a bounded sample
+    rays = systems.lattice_rays(side, 12.0, 0.0, WAVELENGTH)
+    go = oracle.prepared_trace(system.surfaces, materials, rays, keep_all=False, n_threads=cores)
+    warm = oracle.prepared_trace(system.surfaces, materials, rays[:200_000], keep_all=False, n_threads=cores)
+    for _ in range(args.warmup):
+        warm()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        go()
+    dt = time.perf_counter() - t0
+    value = rays.shape[0] * N_SURFACES * args.steps / dt
+    sample = f"{side}x{side} = {rays.shape[0]} rays x {N_SURFACES} surfaces per step, final slab only"
+    line = {"impl": "reference", "metric": "ray_surfaces_per_s_fp64", "value": value, "unit": "ray*surfaces/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "relay10 (BASELINE config 5 system): 10-surface achromat relay, 0.785 um, "
+                                   "collimated Cartesian bundle", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "ray*surfaces/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "ray*surfaces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays-per-gpu", type=float, default=1.25e8)
+    ap.add_argument("--e2e-rays", type=float, default=float(1 << 24))
+    ap.add_argument("--reduce", default="grid", choices=["none", "stats", "grid"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from ray_trace_pb_b200 import _ffi, device as dev, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    L = _ffi.lib()
+    _ffi.require_device()
+
+    system, materials = relay_system()
+    from ray_trace_pb_b200.sharding import shard_range
+    source, side = beam_source(int(args.rays_per_gpu) * world)
+    first, n_rays = shard_range(source.n_rays, rank, world)
+
+    # ---- resident inputs / outputs ---------------------------------------------------------------------
+    rays = source.generate(first=first, count=n_rays, device=local)         # this rank's (N, 8) shard in HBM
+    out = torch.empty((1, n_rays, 8), dtype=torch.float64, device=f"cuda:{local}")
+    reducer = None
+    if args.reduce != "none":
+        # sample just after the second doublet (slab 12), where the relay's beam is collimated: the pupil
+        reducer = dev.Reducer(12, origin=(8.0, 0, 0), grid_n=GRID_N if args.reduce == "grid" else 0,
+                              half_width=8.0, device=local)
+
+    def step():
+        if reducer is not None:
+            reducer.reset()
+        dev.trace_tensor(system.surfaces, materials, rays, keep="last", wavelengths=[WAVELENGTH], reducer=reducer,
+                         out=out)
+        if reducer is not None and world > 1:
+            reducer.allreduce()
+
+    # ---- roofline denominators measured live --------------------------------------------------------------
+    dfma = ctypes.c_double()
+    ms_probe = ctypes.c_double()
+    _ffi.check(L.rtb_measure_dfma_rate(local, ctypes.byref(dfma), ctypes.byref(ms_probe)))
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region -----------------------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = L.rtb_launch_count()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev0.record()
+    for i in range(args.steps):
+        if reducer is not None:
+            reducer.reset()
+        k0[i].record()
+        dev.trace_tensor(system.surfaces, materials, rays, keep="last", wavelengths=[WAVELENGTH], reducer=reducer,
+                         out=out)
+        k1[i].record()
+        if reducer is not None and world > 1:
+            reducer.allreduce()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = L.rtb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kernel_ms = [a.elapsed_time(b) for a, b in zip(k0, k1)]
+    t = torch.tensor([elapsed_ms, statistics.mean(kernel_ms)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, kernel_ms_mean = float(t[0]), float(t[1])
+    total_ray_surfaces = float(source.n_rays) * N_SURFACES * args.steps
+    value = total_ray_surfaces / (elapsed_ms * 1e-3)
+
+    # sanity: the trace did real work (valid rays came out)
+    n_valid = int(torch.isfinite(out[0, :, 0]).sum())
+    stats = reducer.stats() if (reducer is not None and reducer.stats_t is not None) else None
+
+    # ---- end-to-end through the host-buffer C ABI ---------------------------------------------------------------
+    n_e2e = int(args.e2e_rays)
+    e2e_side = int(np.sqrt(n_e2e))
+    n_e2e = e2e_side * e2e_side
+    e2e_src, _ = beam_source(n_e2e * world)
+    e2e_first, n_e2e = shard_range(e2e_src.n_rays, rank, world)
+    host_in = _ffi.pinned_empty((n_e2e, 8))
+    host_in[:] = e2e_src.generate(first=e2e_first, count=n_e2e, device=local).cpu().numpy()
+    host_out = _ffi.pinned_empty((1, n_e2e, 8))
+    for _ in range(2):
+        engine.trace_host(system.surfaces, materials, host_in, keep="last", device=local, out=host_out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        engine.trace_host(system.surfaces, materials, host_in, keep="last", device=local, out=host_out)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = float(e2e_src.n_rays) * N_SURFACES * e2e_steps / float(te[0])
+    assert np.isfinite(host_out[0, n_e2e // 2, 0])
+
+    if rank == 0:
+        rays_per_s_gpu = float(n_rays) / (kernel_ms_mean * 1e-3)
+        achieved_inst = I_ALG_PER_RAY * rays_per_s_gpu
+        line = {
+            "metric": "ray_surfaces_per_s_fp64", "value": value, "unit": "ray*surfaces/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "relay10 (BASELINE config 5 system): 10-surface achromat relay, 0.785 um, "
+                                   "collimated Cartesian bundle, final slab + fused pupil reduction",
+                       "rays_total": source.n_rays, "rays_rank0": n_rays, "surfaces": N_SURFACES, "keep": "last", "reduce": args.reduce,
+                       "grid": GRID_N if args.reduce == "grid" else 0,
+                       "l2": "inputs (8 GB/GPU at the default size) are larger than L2; no flush needed",
+                       "valid_rays_rank0": n_valid, "parity": "fp64 bit-exact mode"},
+            "roofline": {"bound": "fp64", "achieved": achieved_inst / 1e9, "peak": dfma.value / 1e9,
+                         "unit": "G FP64-pipe instr/s", "frac": achieved_inst / dfma.value, "traffic": None,
+                         "peak_source": "DFMA register micro-benchmark run in this process (rtb_measure_dfma_rate)",
+                         "algorithmic_instr_per_ray": I_ALG_PER_RAY, "kernel_ms": kernel_ms_mean,
+                         "flops_form": {"achieved_tflops": F_ALG_PER_RAY * rays_per_s_gpu / 1e12,
+                                        "peak_tflops_fma2": 2 * dfma.value / 1e12},
+                         "hbm": {"achieved": BYTES_PER_RAY * rays_per_s_gpu / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": BYTES_PER_RAY * rays_per_s_gpu / 1e9 / hbm_peak, "peak_source": hbm_src}},
+            "e2e": {"value": e2e_value, "unit": "ray*surfaces/s", "h2d_bytes_per_step": n_e2e * 64,
+                    "d2h_bytes_per_step": n_e2e * 64, "rays_per_gpu_per_step": n_e2e, "steps": e2e_steps,
+                    "api": "rtb_trace_host via engine.trace_host (pinned host buffers, keep='last')"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if stats is not None:
+            line["config"]["reduce_count"] = stats["count"]
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, sample = cpu_baseline_run(cores)
+            line["cpu_baseline"] = {"value": v, "unit": "ray*surfaces/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@
 #ifndef RTB_H
 #define RTB_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -136,7 +137,7 @@ typedef enum rtb_keep_mode {
  *       (min/max slots must be initialised to +inf / -inf by the caller; rtb_reduce_init does all of this)
  *   grid_dev   (3 * grid_n * grid_n doubles, accumulated with atomics):
  *       plane 0: sum cos(phase - phase_ref), plane 1: sum sin(phase - phase_ref), plane 2: count,
- *       cell (iu, iv) at [plane * G*G + iv * G + iu], iu = floor((u + grid_half_width) / cell), cell = 2*half/G;
+ *       cell (iu, iv) at [plane * G*G + iv * G + iu], iu = floor((u + grid_half_width) * (G / (2*grid_half_width)));
  *       rays outside [-half, half) are counted in stats only.
  */
 #define RTB_N_STATS 12
@@ -152,11 +153,16 @@ typedef struct rtb_reduce {
     double *grid_dev;  /* device, 3*G*G, or NULL       */
 } rtb_reduce;
 
+/* rtb_trace_opts.flags */
+#define RTB_FLAG_INTERSECT_ONLY 1 /* the "at surface" slab is Surface.get_intersect's result (raytrace.py:1331-1337,
+                                     1398-1403, 1479-1516, 1580-1584): no front-side cull; a perfect lens blanks
+                                     rays that would have to travel backwards.  Used by the per-surface operator. */
+
 typedef struct rtb_trace_opts {
     int32_t precision; /* rtb_precision */
     int32_t keep_mode; /* rtb_keep_mode */
     int32_t n_keep;
-    int32_t reserved;
+    int32_t flags;
     const int32_t *keep_slabs; /* host, n_keep entries, for RTB_KEEP_LIST */
     const rtb_reduce *reduce;  /* host, optional */
 } rtb_trace_opts;
@@ -238,10 +244,32 @@ int rtb_reduce_init(const rtb_reduce *red, int device, void *stream);
 int rtb_intersect_rays_device(const double *ray1_dev, int64_t n1, const double *ray2_dev, int64_t n2,
                               double *pts_out_dev, int device, void *stream);
 
+/*
+ * replaces propagate_ray2plane, raytrace.py:241-306, with per-ray planes:
+ * rays_dev (N,8); normal_dev (n_normal,3) and center_dev (n_center,3) with n_* in {1, N}; index_dev (N) = the
+ * medium's n(wavelength) per ray (evaluated by the caller's material object); rays_out_dev (N,8); ts_out_dev (N).
+ */
+int rtb_ray2plane_device(const double *rays_dev, int64_t n_rays, const double *normal_dev, int64_t n_normal,
+                         const double *center_dev, int64_t n_center, const double *index_dev,
+                         int exclude_backward, double *rays_out_dev, double *ts_out_dev, int device, void *stream);
+
+/*
+ * Distinct non-NaN wavelength bit patterns of a device ray batch (column 7), for building the host
+ * refractive-index table of a device-resident batch.  table_dev: RTB_MAX_WAVELENGTHS + 1 doubles of scratch on the
+ * device.  On return (after a stream synchronise done inside) wavelengths_host[0..*n_found) holds them in ascending
+ * order; *n_found = RTB_MAX_WAVELENGTHS + 1 means "more than RTB_MAX_WAVELENGTHS".
+ */
+int rtb_distinct_wavelengths_device(const double *rays_dev, int64_t n_rays, double *table_dev,
+                                    double *wavelengths_host, int32_t *n_found, int device, void *stream);
+
+/* page-locked host memory for zero-staging transfers in rtb_trace_host (NULL on failure) */
+void *rtb_host_alloc(size_t bytes);
+void rtb_host_free(void *p);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------------ */
 /*
  * Register-only dependent-chain DFMA micro-benchmark: the FP64-pipe roofline denominator.
- * Returns warp-level... no: thread-level DFMA instructions per second on `device` in *dfma_per_s.
+ * *dfma_per_s = thread-level DFMA instructions per second on `device` (x2 for FLOP/s), best of 5 launches.
  */
 int rtb_measure_dfma_rate(int device, double *dfma_per_s, double *elapsed_ms);
 /* device-to-device copy bandwidth (read+write bytes / s) over `bytes` bytes, for cross-checking MEASURED_PEAKS */

@@ -135,6 +135,27 @@ def trace(surfaces, materials, rays: np.ndarray, keep_all: bool = True, n_thread
     return out
 
 
+def prepared_trace(surfaces, materials, rays: np.ndarray, keep_all: bool = False, n_threads: int = 1):
+    """
+    For timing: do all Python-side packing once and return ``run() -> out`` that only executes the C loop
+    (bench.py's cpu_baseline / --impl reference legs time ``run``).
+    """
+    rays = np.ascontiguousarray(rays, dtype=float)
+    n = rays.shape[0]
+    surf = pack_surfaces(surfaces)
+    ntab, rows = index_table(materials, rays[:, 7])
+    s = len(surfaces)
+    out = np.zeros((2 * s + 1, n, 8) if keep_all else (n, 8))
+    L = lib()
+    rows_p = rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+    def run():
+        L.oracle_trace(_dptr(surf), s, _dptr(ntab), rows_p, _dptr(rays), n, _dptr(out), int(keep_all), int(n_threads))
+        return out
+
+    return run
+
+
 def ray_trace(system, rays, initial_material, final_material, n_threads: int = 1) -> np.ndarray:
     """Same contract as System.ray_trace (raytrace.py:641-661), including (8,), (N,8) and (K,N,8) inputs."""
     materials = [initial_material] + list(system.materials) + [final_material]
@@ -266,16 +287,16 @@ def reduce_stats(slab_rays: np.ndarray, origin, e1, e2, phase_ref: float = 0.0) 
 
 def reduce_grid(slab_rays: np.ndarray, origin, e1, e2, grid_n: int, half_width: float,
                 phase_ref: float = 0.0) -> np.ndarray:
-    """(3, G, G): sum cos, sum sin, count; cell index = floor((u + half) / (2*half/G)), [iv, iu] order."""
+    """(3, G, G): sum cos, sum sin, count; cell index = floor((u + half) * (G / (2*half))), [iv, iu] order."""
     p = slab_rays[:, 0:3] - np.asarray(origin, dtype=float)
     u = p @ np.asarray(e1, dtype=float)
     v = p @ np.asarray(e2, dtype=float)
     ph = slab_rays[:, 6] - phase_ref
     ok = np.isfinite(u) & np.isfinite(v) & np.isfinite(ph)
-    cell = 2 * half_width / grid_n
+    inv_cell = grid_n / (2 * half_width)
     with np.errstate(invalid="ignore"):
-        iu = np.floor((u + half_width) / cell)
-        iv = np.floor((v + half_width) / cell)
+        iu = np.floor((u + half_width) * inv_cell)
+        iv = np.floor((v + half_width) * inv_cell)
         ok &= (iu >= 0) & (iu < grid_n) & (iv >= 0) & (iv < grid_n)
     iu = iu[ok].astype(np.int64)
     iv = iv[ok].astype(np.int64)

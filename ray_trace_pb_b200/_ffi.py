@@ -1,0 +1,165 @@
+"""
+ctypes binding of librtb.so (C ABI in include/rtb.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C ray_trace_pb_b200/csrc`` into
+``ray_trace_pb_b200/_lib/librtb.so``.  There is no CPU fallback: if the library is missing, or no CUDA device is
+visible when a trace is requested, the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "_lib" / "librtb.so"
+
+RTB_ABI_VERSION = 1
+RTB_MAX_SURFACES = 64
+RTB_MAX_WAVELENGTHS = 16
+RTB_N_STATS = 12
+
+RTB_OK = 0
+RTB_ERR_INVALID = -1
+RTB_ERR_UNSUPPORTED = -2
+RTB_ERR_CUDA = -3
+RTB_ERR_NOMEM = -4
+
+SURF_FLAT, SURF_SPHERE, SURF_MIRROR, SURF_PERFECT_LENS = 0, 1, 2, 3
+MAT_CONSTANT, MAT_SELLMEIER, MAT_TABLE_ONLY = 0, 1, 2
+F64_EXACT, F32_FAST = 0, 1
+KEEP_ALL, KEEP_LAST, KEEP_LIST, KEEP_NONE = 0, 1, 2, 3
+SRC_COLLIMATED, SRC_FAN, SRC_GRID = 0, 1, 2
+FLAG_INTERSECT_ONLY = 1
+
+_d3 = C.c_double * 3
+
+
+class RtbSurface(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32),
+                ("center", _d3), ("normal", _d3), ("input_axis", _d3),
+                ("radius", C.c_double), ("radius_sq", C.c_double), ("abs_radius", C.c_double),
+                ("aperture_rad", C.c_double), ("focal_len", C.c_double), ("normal_f", _d3),
+                ("sin_alpha", C.c_double)]
+
+
+class RtbMaterial(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("b", _d3), ("c", _d3), ("n_const", C.c_double)]
+
+
+class RtbSystem(C.Structure):
+    _fields_ = [("n_surfaces", C.c_int32), ("n_wavelengths", C.c_int32),
+                ("surfaces", C.POINTER(RtbSurface)), ("materials", C.POINTER(RtbMaterial)),
+                ("wavelengths", C.POINTER(C.c_double)), ("n_table", C.POINTER(C.c_double))]
+
+
+class RtbReduce(C.Structure):
+    _fields_ = [("slab", C.c_int32), ("grid_n", C.c_int32), ("origin", _d3), ("e1", _d3), ("e2", _d3),
+                ("phase_ref", C.c_double), ("grid_half_width", C.c_double),
+                ("stats_dev", C.c_void_p), ("grid_dev", C.c_void_p)]
+
+
+class RtbTraceOpts(C.Structure):
+    _fields_ = [("precision", C.c_int32), ("keep_mode", C.c_int32), ("n_keep", C.c_int32), ("flags", C.c_int32),
+                ("keep_slabs", C.POINTER(C.c_int32)), ("reduce", C.POINTER(RtbReduce))]
+
+
+class RtbSource(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("n_a", C.c_int64), ("n_b", C.c_int64),
+                ("a_max", C.c_double), ("b_max", C.c_double), ("b_start", C.c_double),
+                ("pt", _d3), ("axis", _d3), ("e1", _d3), ("e2", _d3), ("wavelength", C.c_double)]
+
+
+class RtbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/rtb.h declares (tests check the .so exports all of them)
+EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_count", "rtb_trace_device",
+           "rtb_trace_host", "rtb_trace_source", "rtb_generate_device", "rtb_reduce_init",
+           "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
+           "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_host_alloc", "rtb_host_free"]
+
+
+def lib():
+    """Load librtb.so once; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RtbError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"or `make -C ray_trace_pb_b200/csrc`. There is no CPU fallback.")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i64, i32, dp = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)
+    L.rtb_abi_version.restype = i32
+    L.rtb_last_error.restype = C.c_char_p
+    L.rtb_device_count.restype = i32
+    L.rtb_launch_count.restype = i64
+    L.rtb_trace_device.argtypes = [C.POINTER(RtbSystem), vp, i64, vp, C.POINTER(RtbTraceOpts), i32, vp]
+    L.rtb_trace_host.argtypes = [C.POINTER(RtbSystem), vp, i64, vp, C.POINTER(RtbTraceOpts), i32]
+    L.rtb_trace_source.argtypes = [C.POINTER(RtbSystem), C.POINTER(RtbSource), i64, i64, vp,
+                                   C.POINTER(RtbTraceOpts), i32, vp]
+    L.rtb_generate_device.argtypes = [C.POINTER(RtbSource), i64, i64, vp, i32, vp]
+    L.rtb_reduce_init.argtypes = [C.POINTER(RtbReduce), i32, vp]
+    L.rtb_intersect_rays_device.argtypes = [vp, i64, vp, i64, vp, i32, vp]
+    L.rtb_ray2plane_device.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, vp, vp, i32, vp]
+    L.rtb_distinct_wavelengths_device.argtypes = [vp, i64, vp, dp, C.POINTER(C.c_int32), i32, vp]
+    L.rtb_measure_dfma_rate.argtypes = [i32, dp, dp]
+    L.rtb_measure_copy_bandwidth.argtypes = [i32, i64, dp]
+    L.rtb_host_alloc.argtypes = [C.c_size_t]
+    L.rtb_host_alloc.restype = vp
+    L.rtb_host_free.argtypes = [vp]
+    L.rtb_host_free.restype = None
+    for name in ("rtb_trace_device", "rtb_trace_host", "rtb_trace_source", "rtb_generate_device", "rtb_reduce_init",
+                 "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
+                 "rtb_ray2plane_device", "rtb_distinct_wavelengths_device"):
+        getattr(L, name).restype = i32
+    if L.rtb_abi_version() != RTB_ABI_VERSION:
+        raise RtbError(f"librtb.so ABI {L.rtb_abi_version()} != binding ABI {RTB_ABI_VERSION}; rebuild the library")
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    """Map a negative rtb_status to the Python exception the reference API would raise for that class of error."""
+    if rc == RTB_OK:
+        return
+    msg = lib().rtb_last_error().decode("utf-8", "replace")
+    if rc == RTB_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == RTB_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == RTB_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RtbError(msg)
+
+
+def require_device() -> int:
+    n = lib().rtb_device_count()
+    if n <= 0:
+        raise RtbError("no CUDA device visible: ray_trace_pb_b200 traces only on the GPU (no CPU fallback)")
+    return n
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """A NumPy array in page-locked memory (freed when the array is garbage collected)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib().rtb_host_alloc(max(nbytes, 1))
+    if not ptr:
+        check(RTB_ERR_NOMEM)
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
+    # every view of the returned array reaches `buf` through its .base chain, so the allocation lives as long as
+    # any of them does
+    weakref.finalize(buf, _free_pinned, ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def _free_pinned(ptr):
+    try:
+        lib().rtb_host_free(ptr)
+    except Exception:
+        pass

@@ -1,0 +1,614 @@
+// rtb_api.cu -- the C ABI declared in include/rtb.h: argument checking, prescription packing, launches and the
+// pinned-memory host pipeline.  No ray arithmetic happens here and nothing here runs a trace on the CPU.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "rtb_device.cuh"
+
+namespace rtb {
+cudaError_t launch_trace_f64(const TraceParams &P, int sm_count, cudaStream_t stream);
+cudaError_t launch_trace_f32(const TraceParams &P, int sm_count, cudaStream_t stream);
+cudaError_t launch_generate(const DevSource &src, long long n_rays, double *out, int sm_count, cudaStream_t stream);
+cudaError_t launch_reduce_init(const DevReduce &red, int sm_count, cudaStream_t stream);
+cudaError_t launch_intersect(const double *r1, long long n1, const double *r2, long long n2, double *out,
+                             cudaStream_t stream);
+cudaError_t launch_ray2plane(const double *rays, long long n, const double *normal, long long n_normal,
+                             const double *center, long long n_center, const double *index, int exclude_backward,
+                             double *out, double *ts, cudaStream_t stream);
+cudaError_t run_distinct_wavelengths(const double *rays, long long n, double *table_dev, int capacity,
+                                     double *host_out, int *n_found, int sm_count, cudaStream_t stream);
+cudaError_t run_dfma_probe(int sm_count, double *dfma_per_s, double *elapsed_ms);
+cudaError_t run_copy_probe(long long bytes, double *bytes_per_s);
+} // namespace rtb
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define RTB_CUDA(call)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(RTB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- per-device context: SM count, streams and staging buffers of the host pipeline ------------------------
+constexpr int kSlots = 3;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    double *dev_in = nullptr;
+    double *dev_out = nullptr;
+    double *pin_in = nullptr;
+    double *pin_out = nullptr;
+    size_t dev_in_bytes = 0, dev_out_bytes = 0, pin_in_bytes = 0, pin_out_bytes = 0;
+};
+
+struct DeviceCtx {
+    bool ready = false;
+    int sm_count = 0;
+    Slot slot[kSlots];
+    std::mutex host_path; // one host-buffer trace at a time per device
+};
+
+constexpr int kMaxDevices = 64;
+DeviceCtx g_ctx[kMaxDevices];
+std::mutex g_ctx_mutex;
+
+int get_ctx(int device, DeviceCtx **out)
+{
+    if (device < 0 || device >= kMaxDevices) return fail(RTB_ERR_INVALID, "device index %d out of range", device);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(RTB_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device >= n) return fail(RTB_ERR_INVALID, "device index %d but only %d device(s) visible", device, n);
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    DeviceCtx &c = g_ctx[device];
+    if (!c.ready) {
+        RTB_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
+        c.ready = true;
+    }
+    *out = &c;
+    return RTB_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    int enter(int device)
+    {
+        RTB_CUDA(cudaGetDevice(&prev));
+        if (prev != device) {
+            RTB_CUDA(cudaSetDevice(device));
+            changed = true;
+        }
+        return RTB_OK;
+    }
+    ~DeviceGuard()
+    {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+// ---- packing ------------------------------------------------------------------------------------------------
+int n_out_slabs(const rtb_system *sys, const rtb_trace_opts *opts)
+{
+    switch (opts->keep_mode) {
+    case RTB_KEEP_ALL: return 2 * sys->n_surfaces + 1;
+    case RTB_KEEP_LAST: return 1;
+    case RTB_KEEP_LIST: return opts->n_keep;
+    default: return 0;
+    }
+}
+
+int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TraceParams &P)
+{
+    if (!sys || !opts) return fail(RTB_ERR_INVALID, "system / options pointer is NULL");
+    const int S = sys->n_surfaces;
+    if (S < 0 || S > RTB_MAX_SURFACES)
+        return fail(RTB_ERR_INVALID, "n_surfaces = %d outside [0, %d]", S, RTB_MAX_SURFACES);
+    if (S > 0 && (!sys->surfaces)) return fail(RTB_ERR_INVALID, "surfaces pointer is NULL");
+    if (!sys->materials) return fail(RTB_ERR_INVALID, "materials pointer is NULL (need n_surfaces + 1 media)");
+    if (sys->n_wavelengths < 0 || sys->n_wavelengths > RTB_MAX_WAVELENGTHS)
+        return fail(RTB_ERR_INVALID, "n_wavelengths = %d outside [0, %d]", sys->n_wavelengths, RTB_MAX_WAVELENGTHS);
+    if (sys->n_wavelengths > 0 && (!sys->wavelengths || !sys->n_table))
+        return fail(RTB_ERR_INVALID, "n_wavelengths > 0 needs wavelengths and n_table");
+
+    memset(&P, 0, sizeof(P));
+    P.n_surf = S;
+    P.n_wl = sys->n_wavelengths;
+    for (int k = 0; k < S; k++) {
+        const rtb_surface &a = sys->surfaces[k];
+        if (a.kind < RTB_SURF_FLAT || a.kind > RTB_SURF_PERFECT_LENS)
+            return fail(RTB_ERR_UNSUPPORTED, "surface %d has unknown kind %d", k, a.kind);
+        rtb::DevSurface &d = P.surf[k];
+        d.kind = a.kind;
+        d.cx = a.center[0]; d.cy = a.center[1]; d.cz = a.center[2];
+        d.nx = a.normal[0]; d.ny = a.normal[1]; d.nz = a.normal[2];
+        d.ax = a.input_axis[0]; d.ay = a.input_axis[1]; d.az = a.input_axis[2];
+        d.radius = a.radius; d.radius_sq = a.radius_sq; d.abs_radius = a.abs_radius;
+        d.aperture = a.aperture_rad;
+        d.focal_len = a.focal_len;
+        d.nfx = a.normal_f[0]; d.nfy = a.normal_f[1]; d.nfz = a.normal_f[2];
+        d.sin_alpha = a.sin_alpha;
+    }
+    for (int k = 0; k <= S; k++) {
+        const rtb_material &a = sys->materials[k];
+        if (a.kind < RTB_MAT_CONSTANT || a.kind > RTB_MAT_TABLE_ONLY)
+            return fail(RTB_ERR_INVALID, "medium %d has unknown kind %d", k, a.kind);
+        if (a.kind == RTB_MAT_TABLE_ONLY && sys->n_wavelengths == 0)
+            return fail(RTB_ERR_UNSUPPORTED,
+                        "medium %d can only be evaluated by its host n(); supply a wavelength table "
+                        "(at most %d distinct wavelengths per batch)", k, RTB_MAX_WAVELENGTHS);
+        rtb::DevMaterial &d = P.mat[k];
+        d.kind = a.kind;
+        d.b0 = a.b[0]; d.b1 = a.b[1]; d.b2 = a.b[2];
+        d.c0 = a.c[0]; d.c1 = a.c[1]; d.c2 = a.c[2];
+        d.n_const = a.n_const;
+    }
+    for (int k = 0; k < sys->n_wavelengths; k++) P.wl[k] = sys->wavelengths[k];
+    if (sys->n_wavelengths > 0)
+        memcpy(P.n_tab, sys->n_table, sizeof(double) * (size_t)(sys->n_wavelengths + 1) * (size_t)(S + 1));
+
+    // which slabs go where
+    const int n_slabs = 2 * S + 1;
+    for (int j = 0; j < rtb::kMaxSlabs + 3; j++) P.slab_pos[j] = -1;
+    switch (opts->keep_mode) {
+    case RTB_KEEP_ALL:
+        for (int j = 0; j < n_slabs; j++) P.slab_pos[j] = (int16_t)j;
+        P.any_store = 1;
+        break;
+    case RTB_KEEP_LAST:
+        P.slab_pos[n_slabs - 1] = 0;
+        P.store_last_only = 1;
+        P.any_store = 1;
+        break;
+    case RTB_KEEP_LIST: {
+        if (opts->n_keep < 1 || opts->n_keep > n_slabs || !opts->keep_slabs)
+            return fail(RTB_ERR_INVALID, "keep list needs 1..%d slab indices", n_slabs);
+        int prev = -1;
+        for (int q = 0; q < opts->n_keep; q++) {
+            const int j = opts->keep_slabs[q];
+            if (j < 0 || j >= n_slabs) return fail(RTB_ERR_INVALID, "keep_slabs[%d] = %d outside [0, %d]", q, j, n_slabs - 1);
+            if (j <= prev) return fail(RTB_ERR_INVALID, "keep_slabs must be strictly increasing");
+            P.slab_pos[j] = (int16_t)q;
+            prev = j;
+        }
+        P.any_store = 1;
+        break;
+    }
+    case RTB_KEEP_NONE:
+        break;
+    default:
+        return fail(RTB_ERR_INVALID, "unknown keep_mode %d", opts->keep_mode);
+    }
+    if (opts->precision != RTB_F64_EXACT && opts->precision != RTB_F32_FAST)
+        return fail(RTB_ERR_INVALID, "unknown precision %d", opts->precision);
+
+    P.flags = opts->flags;
+    P.red.slab = -1;
+    if (opts->reduce) {
+        const rtb_reduce &r = *opts->reduce;
+        if (r.slab < 0 || r.slab >= n_slabs) return fail(RTB_ERR_INVALID, "reduce slab %d outside [0, %d]", r.slab, n_slabs - 1);
+        if (r.grid_n < 0 || r.grid_n > 32768) return fail(RTB_ERR_INVALID, "reduce grid_n %d outside [0, 32768]", r.grid_n);
+        if (r.grid_n > 0 && !(r.grid_half_width > 0)) return fail(RTB_ERR_INVALID, "reduce grid_half_width must be > 0");
+        if (r.grid_n > 0 && !r.grid_dev) return fail(RTB_ERR_INVALID, "reduce grid_n > 0 but grid_dev is NULL");
+        rtb::DevReduce &d = P.red;
+        d.slab = r.slab;
+        d.grid_n = r.grid_n;
+        d.ox = r.origin[0]; d.oy = r.origin[1]; d.oz = r.origin[2];
+        d.e1x = r.e1[0]; d.e1y = r.e1[1]; d.e1z = r.e1[2];
+        d.e2x = r.e2[0]; d.e2y = r.e2[1]; d.e2z = r.e2[2];
+        d.phase_ref = r.phase_ref;
+        d.half_width = r.grid_half_width;
+        d.inv_cell = r.grid_n > 0 ? (double)r.grid_n / (2.0 * r.grid_half_width) : 0.0;
+        d.stats = r.stats_dev;
+        d.grid = r.grid_n > 0 ? r.grid_dev : nullptr;
+        if (!d.stats && !d.grid) d.slab = -1;
+    }
+    P.src.kind = -1;
+    return RTB_OK;
+}
+
+int pack_source(const rtb_source *src, long long first, long long count, rtb::DevSource &d)
+{
+    if (!src) return fail(RTB_ERR_INVALID, "source pointer is NULL");
+    if (src->kind < RTB_SRC_COLLIMATED || src->kind > RTB_SRC_GRID)
+        return fail(RTB_ERR_INVALID, "unknown source kind %d", src->kind);
+    if (src->n_a < 1 || src->n_b < 1) return fail(RTB_ERR_INVALID, "source needs n_a >= 1 and n_b >= 1");
+    const long long total = src->n_a * src->n_b;
+    if (first < 0 || count < 0 || first + count > total)
+        return fail(RTB_ERR_INVALID, "ray range [%lld, %lld) outside the source's %lld rays", first, first + count, total);
+    memset(&d, 0, sizeof(d));
+    d.kind = src->kind;
+    d.n_a = src->n_a;
+    d.n_b = src->n_b;
+    d.first = first;
+    // np.linspace(-m, m, n): step = (stop - start) / (n - 1); y = arange(n) * step + start; y[-1] = stop
+    auto lin = [](double m, long long n, double &start, double &step, double &stop) {
+        start = -m;
+        stop = m;
+        const double delta = stop - start;
+        step = (n > 1) ? delta / (double)(n - 1) : delta;
+    };
+    lin(src->a_max, src->n_a, d.a_start, d.a_step, d.a_stop);
+    if (src->kind == RTB_SRC_GRID)
+        lin(src->b_max, src->n_b, d.b_start, d.b_step, d.b_stop);
+    else
+        d.b_start = (src->kind == RTB_SRC_COLLIMATED) ? src->b_start : 0.0;
+    d.px = src->pt[0]; d.py = src->pt[1]; d.pz = src->pt[2];
+    d.axx = src->axis[0]; d.axy = src->axis[1]; d.axz = src->axis[2];
+    d.e1x = src->e1[0]; d.e1y = src->e1[1]; d.e1z = src->e1[2];
+    d.e2x = src->e2[0]; d.e2y = src->e2[1]; d.e2z = src->e2[2];
+    d.wavelength = src->wavelength;
+    return RTB_OK;
+}
+
+int launch(const rtb::TraceParams &P, int precision, int sm_count, cudaStream_t stream)
+{
+    cudaError_t e = (precision == RTB_F32_FAST) ? rtb::launch_trace_f32(P, sm_count, stream)
+                                                : rtb::launch_trace_f64(P, sm_count, stream);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString(e));
+    if (P.n_rays > 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RTB_OK;
+}
+
+int grow_dev(double **p, size_t *have, size_t want)
+{
+    if (*have >= want) return RTB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    if (cudaMalloc(p, want) != cudaSuccess) return fail(RTB_ERR_NOMEM, "cudaMalloc of %zu bytes failed", want);
+    *have = want;
+    return RTB_OK;
+}
+
+int grow_pin(double **p, size_t *have, size_t want)
+{
+    if (*have >= want) return RTB_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *have = 0;
+    if (cudaHostAlloc(p, want, cudaHostAllocDefault) != cudaSuccess)
+        return fail(RTB_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", want);
+    *have = want;
+    return RTB_OK;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+} // namespace
+
+extern "C" {
+
+int rtb_abi_version(void) { return RTB_ABI_VERSION; }
+
+const char *rtb_last_error(void) { return g_err; }
+
+int rtb_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t rtb_launch_count(void) { return g_launches.load(); }
+
+int rtb_trace_device(const rtb_system *sys, const double *rays_in_dev, int64_t n_rays, double *out_dev,
+                     const rtb_trace_opts *opts, int device, void *stream)
+{
+    rtb::TraceParams P;
+    int rc = pack_params(sys, opts, P);
+    if (rc) return rc;
+    if (n_rays < 0) return fail(RTB_ERR_INVALID, "n_rays = %lld is negative", (long long)n_rays);
+    if (n_rays > 0 && !rays_in_dev) return fail(RTB_ERR_INVALID, "rays_in_dev is NULL");
+    if (n_rays > 0 && P.any_store && !out_dev) return fail(RTB_ERR_INVALID, "out_dev is NULL but the keep mode stores rays");
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    P.rays_in = rays_in_dev;
+    P.out = out_dev;
+    P.n_rays = n_rays;
+    P.out_stride = 8 * (long long)n_rays;
+    return launch(P, opts->precision, ctx->sm_count, (cudaStream_t)stream);
+}
+
+int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first_ray, int64_t n_rays,
+                     double *out_dev, const rtb_trace_opts *opts, int device, void *stream)
+{
+    rtb::TraceParams P;
+    int rc = pack_params(sys, opts, P);
+    if (rc) return rc;
+    if ((rc = pack_source(src, first_ray, n_rays, P.src))) return rc;
+    if (n_rays > 0 && P.any_store && !out_dev) return fail(RTB_ERR_INVALID, "out_dev is NULL but the keep mode stores rays");
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    P.rays_in = nullptr;
+    P.out = out_dev;
+    P.n_rays = n_rays;
+    P.out_stride = 8 * (long long)n_rays;
+    return launch(P, opts->precision, ctx->sm_count, (cudaStream_t)stream);
+}
+
+int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_rays, double *out_host,
+                   const rtb_trace_opts *opts, int device)
+{
+    rtb::TraceParams P;
+    int rc = pack_params(sys, opts, P);
+    if (rc) return rc;
+    if (n_rays < 0) return fail(RTB_ERR_INVALID, "n_rays = %lld is negative", (long long)n_rays);
+    if (n_rays == 0) return RTB_OK;
+    if (!rays_in_host) return fail(RTB_ERR_INVALID, "rays_in_host is NULL");
+    const int slabs = n_out_slabs(sys, opts);
+    if (slabs > 0 && !out_host) return fail(RTB_ERR_INVALID, "out_host is NULL but the keep mode stores rays");
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    std::lock_guard<std::mutex> lock(ctx->host_path);
+
+    // chunk so that one chunk's output is ~128 MiB: big enough for PCIe efficiency, small enough to overlap
+    const size_t row = 64;
+    const size_t target = (size_t)128 << 20;
+    long long chunk = (long long)(target / (row * (size_t)std::max(slabs, 1)));
+    chunk = std::max<long long>(chunk, 1 << 14);
+    chunk = std::min<long long>(chunk, 1 << 22);
+    chunk = std::min<long long>(chunk, n_rays);
+    chunk = (chunk + 127) / 128 * 128;
+
+    const bool in_pinned = is_pinned(rays_in_host);
+    const bool out_pinned = slabs > 0 && is_pinned(out_host);
+
+    for (int s = 0; s < kSlots; s++) {
+        Slot &sl = ctx->slot[s];
+        if (!sl.stream) RTB_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!sl.done) RTB_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        if ((rc = grow_dev(&sl.dev_in, &sl.dev_in_bytes, (size_t)chunk * row))) return rc;
+        if (slabs > 0 && (rc = grow_dev(&sl.dev_out, &sl.dev_out_bytes, (size_t)chunk * row * slabs))) return rc;
+        if (!in_pinned && (rc = grow_pin(&sl.pin_in, &sl.pin_in_bytes, (size_t)chunk * row))) return rc;
+        if (slabs > 0 && !out_pinned && (rc = grow_pin(&sl.pin_out, &sl.pin_out_bytes, (size_t)chunk * row * slabs)))
+            return rc;
+    }
+
+    struct Pending {
+        bool active = false;
+        long long r0 = 0, cnt = 0;
+    } pending[kSlots];
+
+    auto retire = [&](int s) -> int {
+        Pending &pd = pending[s];
+        if (!pd.active) return RTB_OK;
+        Slot &sl = ctx->slot[s];
+        RTB_CUDA(cudaEventSynchronize(sl.done));
+        if (slabs > 0 && !out_pinned) {
+            for (int j = 0; j < slabs; j++)
+                memcpy(out_host + ((size_t)j * n_rays + pd.r0) * 8, sl.pin_out + (size_t)j * pd.cnt * 8,
+                       (size_t)pd.cnt * row);
+        }
+        pd.active = false;
+        return RTB_OK;
+    };
+
+    long long n_chunks = (n_rays + chunk - 1) / chunk;
+    for (long long c = 0; c < n_chunks; c++) {
+        const int s = (int)(c % kSlots);
+        if ((rc = retire(s))) return rc;
+        Slot &sl = ctx->slot[s];
+        const long long r0 = c * chunk;
+        const long long cnt = std::min<long long>(chunk, n_rays - r0);
+        const double *src = rays_in_host + (size_t)r0 * 8;
+        if (!in_pinned) {
+            memcpy(sl.pin_in, src, (size_t)cnt * row);
+            src = sl.pin_in;
+        }
+        RTB_CUDA(cudaMemcpyAsync(sl.dev_in, src, (size_t)cnt * row, cudaMemcpyHostToDevice, sl.stream));
+        P.rays_in = sl.dev_in;
+        P.out = sl.dev_out;
+        P.n_rays = cnt;
+        P.out_stride = 8 * cnt;
+        if ((rc = launch(P, opts->precision, ctx->sm_count, sl.stream))) return rc;
+        if (slabs > 0) {
+            if (out_pinned) {
+                // (slabs, cnt, 8) device -> rows [r0, r0+cnt) of every slab of the (slabs, N, 8) host array
+                RTB_CUDA(cudaMemcpy2DAsync(out_host + (size_t)r0 * 8, (size_t)n_rays * row, sl.dev_out,
+                                           (size_t)cnt * row, (size_t)cnt * row, (size_t)slabs,
+                                           cudaMemcpyDeviceToHost, sl.stream));
+            } else {
+                RTB_CUDA(cudaMemcpyAsync(sl.pin_out, sl.dev_out, (size_t)cnt * row * slabs, cudaMemcpyDeviceToHost,
+                                         sl.stream));
+            }
+        }
+        RTB_CUDA(cudaEventRecord(sl.done, sl.stream));
+        pending[s].active = true;
+        pending[s].r0 = r0;
+        pending[s].cnt = cnt;
+    }
+    // drain in issue order
+    for (long long c = n_chunks; c < n_chunks + kSlots; c++)
+        if ((rc = retire((int)(c % kSlots)))) return rc;
+    return RTB_OK;
+}
+
+int rtb_generate_device(const rtb_source *src, int64_t first_ray, int64_t n_rays, double *rays_out_dev, int device,
+                        void *stream)
+{
+    rtb::DevSource d;
+    int rc = pack_source(src, first_ray, n_rays, d);
+    if (rc) return rc;
+    if (n_rays == 0) return RTB_OK;
+    if (!rays_out_dev) return fail(RTB_ERR_INVALID, "rays_out_dev is NULL");
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    cudaError_t e = rtb::launch_generate(d, n_rays, rays_out_dev, ctx->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "generator launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RTB_OK;
+}
+
+int rtb_reduce_init(const rtb_reduce *red, int device, void *stream)
+{
+    if (!red) return fail(RTB_ERR_INVALID, "reduce pointer is NULL");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    rtb::DevReduce d;
+    memset(&d, 0, sizeof(d));
+    d.stats = red->stats_dev;
+    d.grid = red->grid_n > 0 ? red->grid_dev : nullptr;
+    d.grid_n = red->grid_n;
+    if (!d.stats && !d.grid) return RTB_OK;
+    cudaError_t e = rtb::launch_reduce_init(d, ctx->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "reduce-init launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RTB_OK;
+}
+
+int rtb_intersect_rays_device(const double *ray1_dev, int64_t n1, const double *ray2_dev, int64_t n2,
+                              double *pts_out_dev, int device, void *stream)
+{
+    if (n1 < 0 || n2 < 0) return fail(RTB_ERR_INVALID, "negative ray count");
+    if (!(n1 == n2 || n1 == 1 || n2 == 1)) return fail(RTB_ERR_INVALID, "ray1 and ray2 must be the same length");
+    const long long n = std::max<long long>(n1, n2);
+    if (n1 == 0 || n2 == 0) return RTB_OK;
+    if (!ray1_dev || !ray2_dev || !pts_out_dev) return fail(RTB_ERR_INVALID, "NULL device pointer");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    (void)n;
+    cudaError_t e = rtb::launch_intersect(ray1_dev, n1, ray2_dev, n2, pts_out_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "intersect launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RTB_OK;
+}
+
+int rtb_ray2plane_device(const double *rays_dev, int64_t n_rays, const double *normal_dev, int64_t n_normal,
+                         const double *center_dev, int64_t n_center, const double *index_dev, int exclude_backward,
+                         double *rays_out_dev, double *ts_out_dev, int device, void *stream)
+{
+    if (n_rays < 0) return fail(RTB_ERR_INVALID, "n_rays is negative");
+    if (n_rays == 0) return RTB_OK;
+    if (!(n_normal == 1 || n_normal == n_rays) || !(n_center == 1 || n_center == n_rays))
+        return fail(RTB_ERR_INVALID, "normal / center must have 1 or n_rays rows");
+    if (!rays_dev || !normal_dev || !center_dev || !index_dev || !rays_out_dev || !ts_out_dev)
+        return fail(RTB_ERR_INVALID, "NULL device pointer");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    cudaError_t e = rtb::launch_ray2plane(rays_dev, n_rays, normal_dev, n_normal, center_dev, n_center, index_dev,
+                                          exclude_backward, rays_out_dev, ts_out_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "ray2plane launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RTB_OK;
+}
+
+int rtb_distinct_wavelengths_device(const double *rays_dev, int64_t n_rays, double *table_dev,
+                                    double *wavelengths_host, int32_t *n_found, int device, void *stream)
+{
+    if (n_rays < 0) return fail(RTB_ERR_INVALID, "n_rays is negative");
+    if (!table_dev || !wavelengths_host || !n_found) return fail(RTB_ERR_INVALID, "NULL pointer");
+    if (n_rays > 0 && !rays_dev) return fail(RTB_ERR_INVALID, "rays_dev is NULL");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    int found = 0;
+    double vals[RTB_MAX_WAVELENGTHS + 1];
+    cudaError_t e = rtb::run_distinct_wavelengths(rays_dev, n_rays, table_dev, RTB_MAX_WAVELENGTHS + 1, vals, &found,
+                                                  ctx->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "distinct-wavelength scan failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(n_rays > 0 ? 2 : 1, std::memory_order_relaxed);
+    std::sort(vals, vals + found);
+    for (int k = 0; k < found; k++) wavelengths_host[k] = vals[k];
+    *n_found = found;
+    return RTB_OK;
+}
+
+int rtb_measure_dfma_rate(int device, double *dfma_per_s, double *elapsed_ms)
+{
+    if (!dfma_per_s) return fail(RTB_ERR_INVALID, "dfma_per_s is NULL");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    double ms = 0;
+    cudaError_t e = rtb::run_dfma_probe(ctx->sm_count, dfma_per_s, &ms);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "DFMA probe failed: %s", cudaGetErrorString(e));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return RTB_OK;
+}
+
+int rtb_measure_copy_bandwidth(int device, int64_t bytes, double *bytes_per_s)
+{
+    if (!bytes_per_s || bytes <= 0) return fail(RTB_ERR_INVALID, "bad arguments");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    cudaError_t e = rtb::run_copy_probe(bytes, bytes_per_s);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "copy probe failed: %s", cudaGetErrorString(e));
+    return RTB_OK;
+}
+
+void *rtb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(RTB_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void rtb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+} // extern "C"

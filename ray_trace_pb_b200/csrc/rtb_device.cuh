@@ -1,0 +1,109 @@
+// rtb_device.cuh -- device-side records and small helpers shared by the kernels and the C-ABI front end.
+//
+// Data layout in HBM
+//   rays     : (N, 8) float64 rows of 64 B (x y z dx dy dz phase wavelength), the reference's own layout
+//              (raytrace.py:1-5).  One thread owns one ray; a row moves as two 256-bit vector accesses, so a
+//              warp touches 2 KB of contiguous memory with every 32-B sector fully used.
+//   history  : (n_slabs, N, 8), slab-major like the NumPy array System.ray_trace returns.
+//   the prescription (surfaces, media, refractive-index table) lives in the kernel parameter block
+//   (__grid_constant__, constant bank 0): it is read warp-uniformly and is private to each launch, so concurrent
+//   traces of different systems on different streams cannot interfere.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/rtb.h"
+
+namespace rtb {
+
+constexpr int kMaxSurfaces = RTB_MAX_SURFACES;
+constexpr int kMaxMedia = RTB_MAX_SURFACES + 1;
+constexpr int kMaxWavelengths = RTB_MAX_WAVELENGTHS;
+constexpr int kMaxSlabs = 2 * RTB_MAX_SURFACES + 1;
+
+struct DevSurface {
+    double cx, cy, cz;    // center
+    double nx, ny, nz;    // geometric normal (flat / mirror / lens)
+    double ax, ay, az;    // input axis (front-side cull, sphere aperture)
+    double radius, radius_sq, abs_radius;
+    double aperture;
+    double focal_len;
+    double nfx, nfy, nfz; // normal * focal_len
+    double sin_alpha;
+    int32_t kind;
+    int32_t pad;
+};
+
+struct DevMaterial {
+    double b0, b1, b2;
+    double c0, c1, c2;
+    double n_const;
+    int32_t kind;
+    int32_t pad;
+};
+
+struct DevReduce {
+    double ox, oy, oz;
+    double e1x, e1y, e1z;
+    double e2x, e2y, e2z;
+    double phase_ref;
+    double half_width;
+    double inv_cell; // G / (2 * half_width), host computed
+    double *stats;
+    double *grid;
+    int32_t slab; // -1 = no reduction
+    int32_t grid_n;
+};
+
+struct DevSource {
+    double a_start, a_step, a_stop; // linspace pieces: value(i) = i*a_step + a_start, last forced to a_stop
+    double b_start, b_step, b_stop; // GRID: second linspace; FAN / COLLIMATED: azimuth = i * b_step + b_start
+    double px, py, pz;
+    double axx, axy, axz;
+    double e1x, e1y, e1z;
+    double e2x, e2y, e2z;
+    double wavelength;
+    long long n_a, n_b;
+    long long first;
+    int32_t kind; // -1 = rays come from memory
+    int32_t pad;
+};
+
+// Everything one trace launch needs.  ~26 KB: inside the 32,764-byte kernel parameter limit of CUDA 12.1+.
+struct TraceParams {
+    const double *rays_in;
+    double *out;
+    long long n_rays;
+    long long out_stride;       // doubles between output slabs (= 8 * n_rays of the *output* buffer)
+    int32_t n_surf;
+    int32_t n_wl;               // > 0: refractive indices come from n_tab
+    int32_t store_last_only;    // RTB_KEEP_LAST fast flag
+    int32_t any_store;
+    int32_t flags;              // RTB_FLAG_*
+    int32_t pad0;
+    int16_t slab_pos[kMaxSlabs + 3]; // output slab position of trace slab j, -1 = not stored
+    DevReduce red;
+    DevSource src;
+    DevSurface surf[kMaxSurfaces];
+    DevMaterial mat[kMaxMedia];
+    double wl[kMaxWavelengths];
+    double n_tab[(kMaxWavelengths + 1) * kMaxMedia]; // row-major [wavelength row][medium], row n_wl = NaN answer
+};
+
+static_assert(sizeof(TraceParams) < 32764, "TraceParams must fit the kernel parameter space");
+
+// 256-bit global accesses (sm_100+): one ray row = two of these.
+__device__ __forceinline__ void ld256_stream(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(a), "=d"(b), "=d"(c), "=d"(d)
+                 : "l"(p));
+}
+
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+} // namespace rtb

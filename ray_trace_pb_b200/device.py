@@ -1,0 +1,368 @@
+"""
+Device-resident API: the same kernels as ``System.ray_trace`` but with rays, histories and reduction buffers living
+in HBM.  PyTorch is used only as the owner of device memory and streams (``torch.empty(..., device="cuda")``,
+``tensor.data_ptr()``, ``torch.cuda.current_stream()``); every computation is a kernel of librtb.so.
+
+Main pieces
+-----------
+``trace_tensor``      (N, 8) CUDA tensor -> (n_slabs, N, 8) CUDA tensor
+``RaySource``         on-device ``get_ray_fan`` / ``get_collimated_rays`` / Cartesian grid (reference raytrace.py:45-161)
+``trace_source``      source -> trace fused in one kernel: no input bytes at all
+``Reducer``           spot statistics + pupil-grid accumulation fused into the trace (rtb_reduce in include/rtb.h)
+``intersect_rays``, ``propagate_ray2plane``, ``surface_intersect``  the helpers around the trace
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi, engine
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream_ptr(device_index: int) -> int:
+    return _torch().cuda.current_stream(device_index).cuda_stream
+
+
+def _check_rays_tensor(t, what="rays"):
+    torch = _torch()
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError(f"{what} must be a CUDA torch.Tensor")
+    if t.dtype != torch.float64:
+        raise TypeError(f"{what} must be float64, got {t.dtype}")
+    if t.dim() != 2 or t.shape[1] != 8:
+        raise ValueError(f"{what} must have shape (N, 8), got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def distinct_wavelengths_tensor(rays):
+    """Distinct non-NaN wavelengths of a device batch (ascending), or None if more than RTB_MAX_WAVELENGTHS."""
+    torch = _torch()
+    rays = _check_rays_tensor(rays)
+    dev = rays.device.index
+    scratch = torch.empty(_ffi.RTB_MAX_WAVELENGTHS + 1, dtype=torch.float64, device=rays.device)
+    host = np.empty(_ffi.RTB_MAX_WAVELENGTHS + 1, dtype=np.float64)
+    found = C.c_int32(0)
+    rc = _ffi.lib().rtb_distinct_wavelengths_device(rays.data_ptr(), rays.shape[0], scratch.data_ptr(),
+                                                    host.ctypes.data_as(C.POINTER(C.c_double)), C.byref(found), dev,
+                                                    _stream_ptr(dev))
+    _ffi.check(rc)
+    if found.value > _ffi.RTB_MAX_WAVELENGTHS:
+        return None
+    return host[:found.value].copy()
+
+
+def _system_for(surfaces, materials, wavelengths):
+    """wavelengths: array of distinct values, None -> in-kernel Sellmeier."""
+    if wavelengths is not None:
+        wavelengths = np.asarray(wavelengths, dtype=np.float64).reshape(-1)
+        if wavelengths.size == 0:
+            wavelengths = None
+    if wavelengths is None and any(engine.pack_material(m).kind == _ffi.MAT_TABLE_ONLY for m in materials):
+        wavelengths = np.array([1.0])   # batch without a valid wavelength: only the NaN row is ever used
+    return engine.pack_system(surfaces, materials, wavelengths)
+
+
+def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelengths="auto", reducer=None,
+                 out=None, flags: int = 0):
+    """
+    rays: (N, 8) float64 CUDA tensor; ``materials`` = [initial] + system.materials + [final].
+    wavelengths: "auto" scans the batch on the device for its distinct wavelengths (one extra pass over column 7);
+    pass the known values (e.g. ``[0.785]``) to skip that, or None to force in-kernel Sellmeier evaluation.
+    Returns a (n_slabs, N, 8) CUDA tensor on the same device (None for keep="none").  Enqueued on the current stream.
+    """
+    torch = _torch()
+    rays = _check_rays_tensor(rays)
+    dev = rays.device.index
+    if isinstance(wavelengths, str):
+        if wavelengths != "auto":
+            raise ValueError("wavelengths must be 'auto', None or a sequence of values")
+        wavelengths = distinct_wavelengths_tensor(rays)
+    packed = _system_for(surfaces, materials, wavelengths)
+    mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
+    opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
+    opts.flags = flags
+    n = rays.shape[0]
+    if n_out == 0:
+        out = None
+    elif out is None:
+        out = torch.empty((n_out, n, 8), dtype=torch.float64, device=rays.device)
+    elif tuple(out.shape) != (n_out, n, 8) or out.dtype != torch.float64 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float64 tensor of shape {(n_out, n, 8)}")
+    rc = _ffi.lib().rtb_trace_device(C.byref(packed.sys), rays.data_ptr(), n, out.data_ptr() if out is not None else None,
+                                     C.byref(opts), dev, _stream_ptr(dev))
+    _ffi.check(rc)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# ray sources
+# ----------------------------------------------------------------------------------------------------------
+@dataclass
+class RaySource:
+    """
+    Description of a structured ray bundle that the device can enumerate by index (rtb_source in include/rtb.h).
+    Build one with :meth:`fan`, :meth:`collimated` or :meth:`grid`; the transverse basis is computed here with the
+    reference's own expressions (raytrace.py:79-81, 135-144).
+    """
+    kind: int
+    n_a: int
+    n_b: int
+    a_max: float
+    b_max: float
+    b_start: float
+    pt: np.ndarray
+    axis: np.ndarray
+    e1: np.ndarray
+    e2: np.ndarray
+    wavelength: float
+
+    @property
+    def n_rays(self) -> int:
+        return self.n_a * self.n_b
+
+    @classmethod
+    def fan(cls, pt, theta_max, n_thetas, wavelength, nphis=1, center_ray=(0, 0, 1)):
+        """get_ray_fan (raytrace.py:45-96): index = i_phi * n_thetas + i_theta"""
+        from .raytrace import _transverse_basis
+        axis = np.array(center_ray, dtype=float)
+        if np.linalg.norm(axis) != 1:
+            raise ValueError("center_ray must be a unit vector")
+        e1, e2 = _transverse_basis(axis, fallback=False)
+        return cls(_ffi.SRC_FAN, int(n_thetas), int(nphis), float(theta_max), 0.0, 0.0,
+                   np.array(pt, dtype=float).reshape(3), axis, e1, e2, float(wavelength))
+
+    @classmethod
+    def collimated(cls, pt, displacement_max, n_disps, wavelength, nphis=1, phi_start=0., normal=(0, 0, 1)):
+        """get_collimated_rays (raytrace.py:99-161): index = i_disp * nphis + i_phi"""
+        from .raytrace import _transverse_basis
+        if np.abs(np.linalg.norm(normal) - 1) > 1e-12:
+            raise ValueError("normal must be a normalized vector")
+        axis = np.array(normal, dtype=float).reshape(3)
+        e1, e2 = _transverse_basis(axis, fallback=True)
+        return cls(_ffi.SRC_COLLIMATED, int(n_disps), int(nphis), float(displacement_max), 0.0, float(phi_start),
+                   np.array(pt, dtype=float).reshape(3), axis, e1, e2, float(wavelength))
+
+    @classmethod
+    def grid(cls, pt, half_width_u, n_u, wavelength, half_width_v=None, n_v=None, normal=(0, 0, 1)):
+        """Cartesian grid of parallel rays, u along e1 and v along e2: index = i_v * n_u + i_u"""
+        from .raytrace import _transverse_basis
+        if np.abs(np.linalg.norm(normal) - 1) > 1e-12:
+            raise ValueError("normal must be a normalized vector")
+        axis = np.array(normal, dtype=float).reshape(3)
+        e1, e2 = _transverse_basis(axis, fallback=True)
+        return cls(_ffi.SRC_GRID, int(n_u), int(n_u if n_v is None else n_v), float(half_width_u),
+                   float(half_width_u if half_width_v is None else half_width_v), 0.0,
+                   np.array(pt, dtype=float).reshape(3), axis, e1, e2, float(wavelength))
+
+    @property
+    def struct(self) -> _ffi.RtbSource:
+        s = _ffi.RtbSource()
+        s.kind, s.n_a, s.n_b = self.kind, self.n_a, self.n_b
+        s.a_max, s.b_max, s.b_start = self.a_max, self.b_max, self.b_start
+        s.pt = engine._v3(self.pt)
+        s.axis = engine._v3(self.axis)
+        s.e1 = engine._v3(self.e1)
+        s.e2 = engine._v3(self.e2)
+        s.wavelength = self.wavelength
+        return s
+
+    def generate(self, first: int = 0, count: int | None = None, device: int = 0):
+        """Materialise rays [first, first+count) as an (count, 8) CUDA tensor."""
+        torch = _torch()
+        _ffi.require_device()
+        count = self.n_rays - first if count is None else count
+        out = torch.empty((count, 8), dtype=torch.float64, device=f"cuda:{device}")
+        src = self.struct
+        rc = _ffi.lib().rtb_generate_device(C.byref(src), first, count, out.data_ptr(), device, _stream_ptr(device))
+        _ffi.check(rc)
+        return out
+
+
+def trace_source(surfaces, materials, source: RaySource, first: int = 0, count: int | None = None, keep="last",
+                 precision="f64", reducer=None, device: int = 0, out=None):
+    """
+    Generate-and-trace in one kernel: rays [first, first+count) of ``source`` never exist in memory.
+    The refractive-index table is built from the source's single wavelength.
+    """
+    torch = _torch()
+    _ffi.require_device()
+    count = source.n_rays - first if count is None else count
+    packed = _system_for(surfaces, materials, [source.wavelength] if np.isfinite(source.wavelength) else None)
+    mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
+    opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
+    if n_out == 0:
+        out = None
+    elif out is None:
+        out = torch.empty((n_out, count, 8), dtype=torch.float64, device=f"cuda:{device}")
+    src = source.struct
+    rc = _ffi.lib().rtb_trace_source(C.byref(packed.sys), C.byref(src), first, count,
+                                     out.data_ptr() if out is not None else None, C.byref(opts), device,
+                                     _stream_ptr(device))
+    _ffi.check(rc)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fused reductions
+# ----------------------------------------------------------------------------------------------------------
+class Reducer:
+    """
+    Spot statistics and pupil-grid accumulation sampled at one slab of the trace, fused into the trace kernel.
+
+    u = (p - origin).e1, v = (p - origin).e2.  ``stats`` is the 12-vector documented in include/rtb.h; ``grid`` is a
+    (3, G, G) tensor: sum cos(phase - phase_ref), sum sin(phase - phase_ref), count (indexed [plane, iv, iu]).
+    Accumulates across calls until :meth:`reset`.  ``allreduce()`` sums over the ranks of the default
+    ``torch.distributed`` group (NCCL over NVLink): the only communication of a multi-GPU trace.
+    """
+
+    def __init__(self, slab: int, origin=(0, 0, 0), e1=(1, 0, 0), e2=(0, 1, 0), grid_n: int = 0,
+                 half_width: float = 1.0, phase_ref: float = 0.0, stats: bool = True, device: int = 0):
+        torch = _torch()
+        _ffi.require_device()
+        self.device = device
+        self.slab = int(slab)
+        self.grid_n = int(grid_n)
+        self.stats_t = torch.empty(_ffi.RTB_N_STATS, dtype=torch.float64, device=f"cuda:{device}") if stats else None
+        self.grid_t = (torch.empty((3, grid_n, grid_n), dtype=torch.float64, device=f"cuda:{device}")
+                       if grid_n > 0 else None)
+        s = _ffi.RtbReduce()
+        s.slab = self.slab
+        s.grid_n = self.grid_n
+        s.origin = engine._v3(origin)
+        s.e1 = engine._v3(e1)
+        s.e2 = engine._v3(e2)
+        s.phase_ref = float(phase_ref)
+        s.grid_half_width = float(half_width)
+        s.stats_dev = self.stats_t.data_ptr() if stats else None
+        s.grid_dev = self.grid_t.data_ptr() if grid_n > 0 else None
+        self.struct = s
+        self.reset()
+
+    def resolve_slab(self, n_slabs: int):
+        """allow negative slab indices once the system is known"""
+        if self.struct.slab < 0:
+            self.struct.slab += n_slabs
+        return self
+
+    def reset(self):
+        rc = _ffi.lib().rtb_reduce_init(C.byref(self.struct), self.device, _stream_ptr(self.device))
+        _ffi.check(rc)
+
+    def allreduce(self):
+        from .sharding import allreduce_grid, allreduce_stats
+        if self.grid_t is not None:
+            allreduce_grid(self.grid_t)
+        if self.stats_t is not None:
+            allreduce_stats(self.stats_t)
+        return self
+
+    def stats(self) -> dict:
+        """Host copy of the statistics with the derived centroid / RMS radius / RMS wavefront error."""
+        v = self.stats_t.cpu().numpy()
+        return summarize_stats(v)
+
+    @property
+    def grid(self):
+        return self.grid_t
+
+
+def summarize_stats(v: np.ndarray) -> dict:
+    n = v[0]
+    out = {"count": int(n), "raw": v.copy()}
+    if n > 0:
+        mu, mv = v[1] / n, v[2] / n
+        out["centroid"] = (mu, mv)
+        out["rms_radius"] = float(np.sqrt(max(v[3] / n - mu * mu + v[4] / n - mv * mv, 0.0)))
+        mp = v[6] / n
+        out["mean_phase"] = mp
+        out["rms_phase"] = float(np.sqrt(max(v[7] / n - mp * mp, 0.0)))
+        out["u_range"] = (v[8], v[9])
+        out["v_range"] = (v[10], v[11])
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# helpers around the trace
+# ----------------------------------------------------------------------------------------------------------
+def _to_device(a, device=0):
+    torch = _torch()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=f"cuda:{device}", dtype=torch.float64).contiguous(), True
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    return torch.from_numpy(arr).to(f"cuda:{device}"), False
+
+
+def intersect_rays(ray1, ray2, device: int = 0):
+    """intersect_rays (raytrace.py:164-238) on the device.  NumPy in -> NumPy (N, 3) out; CUDA tensors stay tensors."""
+    torch = _torch()
+    _ffi.require_device()
+    as_np = not (isinstance(ray1, torch.Tensor) or isinstance(ray2, torch.Tensor))
+    if as_np:
+        ray1 = np.atleast_2d(np.asarray(ray1, dtype=np.float64))
+        ray2 = np.atleast_2d(np.asarray(ray2, dtype=np.float64))
+    else:
+        ray1 = ray1 if ray1.dim() == 2 else ray1.reshape(1, -1)
+        ray2 = ray2 if ray2.dim() == 2 else ray2.reshape(1, -1)
+        if isinstance(ray1, torch.Tensor) and ray1.is_cuda:
+            device = ray1.device.index
+    n1, n2 = len(ray1), len(ray2)
+    if not (n1 == n2 or n1 == 1 or n2 == 1):
+        raise ValueError("ray1 and ray2 must be the same length")
+    t1, _ = _to_device(ray1, device)
+    t2, _ = _to_device(ray2, device)
+    n = max(n1, n2)
+    out = torch.empty((n, 3), dtype=torch.float64, device=f"cuda:{device}")
+    rc = _ffi.lib().rtb_intersect_rays_device(t1.data_ptr(), n1, t2.data_ptr(), n2, out.data_ptr(), device,
+                                              _stream_ptr(device))
+    _ffi.check(rc)
+    return out.cpu().numpy() if as_np else out
+
+
+def propagate_ray2plane(rays, normal, center, material, exclude_backward_propagation: bool = False, device: int = 0):
+    """propagate_ray2plane (raytrace.py:241-306): returns (rays_out (N, 8), ts (N,)) as NumPy arrays."""
+    torch = _torch()
+    _ffi.require_device()
+    rays = np.atleast_2d(np.array(rays, dtype=np.float64, copy=True))
+    n = rays.shape[0]
+    normal = np.atleast_2d(np.array(normal, dtype=np.float64).squeeze())
+    center = np.atleast_2d(np.array(center, dtype=np.float64).squeeze())
+    for name, arr in (("normal", normal), ("center", center)):
+        if arr.shape[-1] != 3 or arr.shape[0] not in (1, n):
+            raise ValueError(f"{name} must be broadcastable to ({n}, 3)")
+    with np.errstate(all="ignore"):
+        index = np.broadcast_to(np.asarray(material.n(rays[:, 7]), dtype=np.float64).reshape(-1), (n,))
+    t_rays, _ = _to_device(rays, device)
+    t_n, _ = _to_device(normal, device)
+    t_c, _ = _to_device(center, device)
+    t_i, _ = _to_device(np.ascontiguousarray(index), device)
+    out = torch.empty((n, 8), dtype=torch.float64, device=f"cuda:{device}")
+    ts = torch.empty((n,), dtype=torch.float64, device=f"cuda:{device}")
+    rc = _ffi.lib().rtb_ray2plane_device(t_rays.data_ptr(), n, t_n.data_ptr(), normal.shape[0], t_c.data_ptr(),
+                                         center.shape[0], t_i.data_ptr(), int(bool(exclude_backward_propagation)),
+                                         out.data_ptr(), ts.data_ptr(), device, _stream_ptr(device))
+    _ffi.check(rc)
+    return out.cpu().numpy(), ts.cpu().numpy()
+
+
+def surface_intersect(surface, rays, material, device: int = 0):
+    """Surface.get_intersect (raytrace.py:1331-1337, 1398-1403, 1479-1516, 1580-1584) as a one-surface device trace."""
+    rays = np.atleast_2d(np.asarray(rays, dtype=np.float64))
+    uniq = engine.choose_wavelength_table([material, material], rays[:, 7])
+    packed = engine.pack_system([surface], [material, material], uniq)
+    mode, idx, n_out = engine.resolve_keep([1], packed.n_slabs)
+    opts = engine.make_opts(mode, idx, "f64")
+    opts.flags = _ffi.FLAG_INTERSECT_ONLY
+    rays = np.ascontiguousarray(rays)
+    out = np.empty((1, rays.shape[0], 8))
+    _ffi.require_device()
+    rc = _ffi.lib().rtb_trace_host(C.byref(packed.sys), rays.ctypes.data, rays.shape[0], out.ctypes.data,
+                                   C.byref(opts), device)
+    _ffi.check(rc)
+    return out[0]

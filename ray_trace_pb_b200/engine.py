@@ -1,0 +1,224 @@
+"""
+Host side of the trace: turns surface / material objects into the POD records of include/rtb.h and calls the C ABI.
+
+Nothing in this module does ray arithmetic.  The only numerical work on the host is what the reference also does
+per *system* rather than per ray: evaluating ``material.n()`` on the batch's distinct wavelengths (a handful of
+numbers) and the per-surface constants ``radius**2``, ``abs(radius)``, ``normal*focal_len``, ``sin(alpha)``,
+computed with the very Python expressions the reference uses so the kernel starts from identical bits
+(reference raytrace.py:1499, 1528, 1683, 1758).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _ffi
+from .materials import KIND_TABLE_ONLY
+
+SLAB_LAST = -1
+
+
+# ----------------------------------------------------------------------------------------------------------
+# packing
+# ----------------------------------------------------------------------------------------------------------
+def _v3(x):
+    a = np.asarray(x, dtype=np.float64).reshape(-1)
+    if a.size != 3:
+        raise ValueError(f"expected a 3-vector, got shape {np.shape(x)}")
+    return (C.c_double * 3)(float(a[0]), float(a[1]), float(a[2]))
+
+
+def pack_surface(s) -> _ffi.RtbSurface:
+    rec = getattr(s, "device_record", None)
+    if rec is None:
+        raise NotImplementedError(
+            f"{type(s).__name__} has no device_record(): only FlatSurface, SphericalSurface, PlaneMirror and "
+            f"PerfectLens (and subclasses that keep their geometry) can be traced; there is no CPU fallback")
+    d = rec()
+    out = _ffi.RtbSurface()
+    out.kind = d["kind"]
+    out.center = _v3(d["center"])
+    out.normal = _v3(d["normal"])
+    out.input_axis = _v3(d["input_axis"])
+    out.radius = d.get("radius", 0.0)
+    out.radius_sq = d.get("radius_sq", 0.0)
+    out.abs_radius = d.get("abs_radius", 0.0)
+    out.aperture_rad = d["aperture_rad"]
+    out.focal_len = d.get("focal_len", 0.0)
+    out.normal_f = _v3(d.get("normal_f", (0.0, 0.0, 0.0)))
+    out.sin_alpha = d.get("sin_alpha", 0.0)
+    return out
+
+
+def pack_material(m) -> _ffi.RtbMaterial:
+    rec = getattr(m, "device_record", None)
+    out = _ffi.RtbMaterial()
+    if rec is None:
+        # a foreign object that only offers n(): host table only
+        out.kind = KIND_TABLE_ONLY
+        out.n_const = float("nan")
+        return out
+    kind, b, c, n_const = rec()
+    out.kind = kind
+    out.b = (C.c_double * 3)(*b)
+    out.c = (C.c_double * 3)(*c)
+    out.n_const = n_const
+    return out
+
+
+def distinct_wavelengths(wl: np.ndarray, limit: int):
+    """
+    Distinct non-NaN bit patterns of ``wl`` in order of first appearance, or None if there are more than ``limit``.
+    O(N * distinct) with vectorised passes: typical batches carry 1-3 wavelengths.
+    """
+    bits = np.ascontiguousarray(wl, dtype=np.float64).view(np.int64)
+    bits = bits[~np.isnan(wl)]
+    found = []
+    while bits.size:
+        if len(found) == limit:
+            return None
+        v = bits[0]
+        found.append(v)
+        bits = bits[bits != v]
+    return np.array(found, dtype=np.int64).view(np.float64)
+
+
+def index_table(materials, wavelengths: np.ndarray) -> np.ndarray:
+    """
+    (U + 1, M) table: row u = [m.n(wavelengths[u]) for m in materials], last row = the materials' answer to a NaN
+    wavelength.  Each material's own ``n`` is called once on the whole vector, as the reference calls it on arrays.
+    """
+    query = np.concatenate((np.asarray(wavelengths, dtype=np.float64).reshape(-1), [np.nan]))
+    table = np.empty((query.size, len(materials)), dtype=np.float64)
+    with np.errstate(all="ignore"):
+        for j, m in enumerate(materials):
+            try:
+                col = np.asarray(m.n(query), dtype=np.float64).reshape(-1)
+            except Exception:
+                col = np.full(query.size, np.nan)
+                col[:-1] = np.asarray(m.n(query[:-1]), dtype=np.float64).reshape(-1)
+            if col.size != query.size:
+                raise ValueError(f"{type(m).__name__}.n() returned {col.size} values for {query.size} wavelengths")
+            table[:, j] = col
+    return table
+
+
+@dataclass
+class PackedSystem:
+    """RtbSystem plus the Python objects that own the memory it points to."""
+    sys: _ffi.RtbSystem
+    n_surfaces: int
+    keep: list = field(default_factory=list)
+
+    @property
+    def n_slabs(self) -> int:
+        return 2 * self.n_surfaces + 1
+
+
+def pack_system(surfaces, materials, wavelengths=None) -> PackedSystem:
+    """
+    ``materials`` is the full list [initial] + system.materials + [final] (reference raytrace.py:653).
+    ``wavelengths``: distinct wavelengths of the batch (-> host refractive-index table) or None (-> the kernel
+    evaluates Sellmeier / constant media per ray).
+    """
+    S = len(surfaces)
+    if len(materials) != S + 1:
+        raise ValueError("length of materials should be len(surfaces) + 1")
+    if S > _ffi.RTB_MAX_SURFACES:
+        raise ValueError(f"at most {_ffi.RTB_MAX_SURFACES} surfaces per trace, got {S}")
+    surf_arr = (_ffi.RtbSurface * max(S, 1))(*[pack_surface(s) for s in surfaces])
+    mat_arr = (_ffi.RtbMaterial * (S + 1))(*[pack_material(m) for m in materials])
+    sys = _ffi.RtbSystem()
+    sys.n_surfaces = S
+    sys.surfaces = C.cast(surf_arr, C.POINTER(_ffi.RtbSurface))
+    sys.materials = C.cast(mat_arr, C.POINTER(_ffi.RtbMaterial))
+    keep = [surf_arr, mat_arr]
+    if wavelengths is not None:
+        wavelengths = np.ascontiguousarray(wavelengths, dtype=np.float64).reshape(-1)
+        if wavelengths.size > _ffi.RTB_MAX_WAVELENGTHS:
+            raise ValueError(f"at most {_ffi.RTB_MAX_WAVELENGTHS} tabulated wavelengths")
+    if wavelengths is not None and wavelengths.size > 0:
+        table = np.ascontiguousarray(index_table(materials, wavelengths))
+        sys.n_wavelengths = wavelengths.size
+        sys.wavelengths = wavelengths.ctypes.data_as(C.POINTER(C.c_double))
+        sys.n_table = table.ctypes.data_as(C.POINTER(C.c_double))
+        keep += [wavelengths, table]
+    else:
+        sys.n_wavelengths = 0
+        bad = [type(m).__name__ for m, r in zip(materials, mat_arr) if r.kind == KIND_TABLE_ONLY]
+        if bad:
+            raise NotImplementedError(
+                f"media {sorted(set(bad))} define their own n(); they are evaluated on the host per distinct wavelength, "
+                f"which needs at most {_ffi.RTB_MAX_WAVELENGTHS} distinct wavelengths per batch (no CPU fallback)")
+    return PackedSystem(sys, S, keep)
+
+
+def resolve_keep(keep, n_slabs: int):
+    """-> (keep_mode, int32 array or None, n_out_slabs)"""
+    if isinstance(keep, str):
+        if keep == "all":
+            return _ffi.KEEP_ALL, None, n_slabs
+        if keep == "last":
+            return _ffi.KEEP_LAST, None, 1
+        if keep == "none":
+            return _ffi.KEEP_NONE, None, 0
+        raise ValueError(f"keep must be 'all', 'last', 'none' or a list of slab indices, got {keep!r}")
+    idx = [int(k) for k in keep]
+    idx = [k + n_slabs if k < 0 else k for k in idx]
+    if any(k < 0 or k >= n_slabs for k in idx):
+        raise ValueError(f"slab indices must lie in [-{n_slabs}, {n_slabs})")
+    if any(b <= a for a, b in zip(idx, idx[1:])):
+        raise ValueError("slab indices must be strictly increasing")
+    if not idx:
+        return _ffi.KEEP_NONE, None, 0
+    return _ffi.KEEP_LIST, np.array(idx, dtype=np.int32), len(idx)
+
+
+def make_opts(keep_mode, keep_idx, precision="f64", reduce=None):
+    opts = _ffi.RtbTraceOpts()
+    opts.precision = {"f64": _ffi.F64_EXACT, "f32": _ffi.F32_FAST}[precision]
+    opts.keep_mode = keep_mode
+    if keep_idx is not None:
+        opts.n_keep = len(keep_idx)
+        opts.keep_slabs = keep_idx.ctypes.data_as(C.POINTER(C.c_int32))
+    if reduce is not None:
+        opts.reduce = C.pointer(reduce)
+    return opts
+
+
+# ----------------------------------------------------------------------------------------------------------
+# host-buffer trace (the drop-in call)
+# ----------------------------------------------------------------------------------------------------------
+def choose_wavelength_table(materials, wl_column: np.ndarray):
+    """Distinct wavelengths for the host table, or None when the kernel should evaluate n() itself."""
+    uniq = distinct_wavelengths(wl_column, _ffi.RTB_MAX_WAVELENGTHS)
+    if uniq is not None and uniq.size == 0:
+        uniq = None if all(pack_material(m).kind != KIND_TABLE_ONLY for m in materials) else np.array([1.0])
+    return uniq
+
+
+def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64", device: int = 0,
+               reduce=None, out: np.ndarray | None = None) -> np.ndarray:
+    """
+    rays: (N, 8) float64 host array -> (n_out_slabs, N, 8) float64 host array.
+    ``materials`` = [initial] + system.materials + [final].
+    """
+    _ffi.require_device()
+    rays = np.ascontiguousarray(rays, dtype=np.float64)
+    if rays.ndim != 2 or rays.shape[1] != 8:
+        raise ValueError(f"rays must have shape (N, 8), got {rays.shape}")
+    n = rays.shape[0]
+    uniq = choose_wavelength_table(materials, rays[:, 7])
+    packed = pack_system(surfaces, materials, uniq)
+    mode, idx, n_out = resolve_keep(keep, packed.n_slabs)
+    opts = make_opts(mode, idx, precision, reduce)
+    if out is None:
+        out = np.empty((n_out, n, 8), dtype=np.float64)
+    elif out.shape != (n_out, n, 8) or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError(f"out must be a C-contiguous float64 array of shape {(n_out, n, 8)}")
+    rc = _ffi.lib().rtb_trace_host(C.byref(packed.sys), rays.ctypes.data, n, out.ctypes.data if n_out else None,
+                                   C.byref(opts), device)
+    _ffi.check(rc)
+    return out

@@ -1,0 +1,64 @@
+"""
+Multi-GPU layer: rays are independent for the whole trace, so a job shards by contiguous ray-index range over the
+ranks (one process per GPU) with no communication during the trace; the only exchange is the all-reduce of reduced
+products (pupil / PSF grid, statistics) afterwards -- ``Reducer.allreduce`` (NCCL over NVLink on GPUs).
+
+The helpers here are backend-agnostic (they also run under ``gloo`` on CPU, which is how the CPU test-suite covers
+the N > 1 logic).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """
+    Contiguous range [first, first + count) of rank ``rank``: the first ``n_items % world`` ranks get one extra item,
+    so the shards cover [0, n_items) exactly once and differ by at most one item.
+    """
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} / world {world}")
+    base, extra = divmod(int(n_items), world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def allreduce_stats(stats, dist=None):
+    """
+    Combine RTB_N_STATS vectors over the ranks of the default process group: entries 0-7 are sums, 8/10 minima,
+    9/11 maxima (include/rtb.h).  ``stats`` is a float64 torch tensor on the backend's device; modified in place.
+    """
+    if dist is None:
+        import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return stats
+    sums = stats[0:8].clone()
+    mins = stats[[8, 10]].clone()
+    maxs = stats[[9, 11]].clone()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dist.all_reduce(mins, op=dist.ReduceOp.MIN)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+    stats[0:8] = sums
+    stats[8], stats[10] = mins[0], mins[1]
+    stats[9], stats[11] = maxs[0], maxs[1]
+    return stats
+
+
+def allreduce_grid(grid, dist=None):
+    """Sum a (3, G, G) pupil grid over the ranks, in place."""
+    if dist is None:
+        import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return grid
+    dist.all_reduce(grid, op=dist.ReduceOp.SUM)
+    return grid
+
+
+def merge_stats_host(parts) -> np.ndarray:
+    """NumPy version of the same merge (used to check the collective path)."""
+    parts = np.asarray(parts, dtype=np.float64)
+    out = np.empty(12)
+    out[0:8] = parts[:, 0:8].sum(axis=0)
+    out[[8, 10]] = parts[:, [8, 10]].min(axis=0)
+    out[[9, 11]] = parts[:, [9, 11]].max(axis=0)
+    return out

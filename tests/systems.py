@@ -84,6 +84,8 @@ def rebuild_material(d, rtm):
 
 
 def rebuild_system(desc, rt, rtm):
+    if isinstance(desc, np.ndarray):
+        desc = desc.item()
     if isinstance(desc, (str, bytes, np.str_)):
         desc = json.loads(str(desc))
     surfaces = []

@@ -1,0 +1,348 @@
+"""
+GPU parity tests (`-m gpu`): the CUDA path, called through the drop-in API and the C ABI, against
+  (1) the golden vectors written from the reference itself (bit for bit),
+  (2) the CPU oracle on larger seeded batches (bit for bit),
+  (3) sha256 pins of reference outputs at 1e5 rays,
+and the project's own reductions / sources against their NumPy definitions (1e-10 relative: atomics reorder sums).
+
+Bar: fp64 mode is BIT-EXACT for positions, directions, phase, wavelength and NaN masks (north star asks 1e-10).
+"""
+import numpy as np
+import pytest
+
+import parity
+import systems
+from conftest import load_golden
+from test_oracle_golden import BIG, _tables_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import ray_trace_pb_b200.device as dev
+    return dev
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", sorted(systems.CASES))
+def test_golden_history(name, rt, rtm):
+    g = load_golden(name)
+    system, m_in, m_out = systems.rebuild_system(g["system"], rt, rtm)
+    got = system.ray_trace(g["rays_in"], m_in, m_out)
+    materials = [m_in] + system.materials + [m_out]
+    if name in systems.POWER_DEPENDENT and not _tables_match(g, materials):
+        parity.assert_close_same_mask(got, g["history"], rtol=1e-10, what=name)
+    else:
+        parity.assert_bit_identical(got, g["history"], name)
+
+
+def test_input_shapes(rt, rtm):
+    g = load_golden("input_shapes")
+    system, m_in, m_out = systems.rebuild_system(g["system"], rt, rtm)
+    parity.assert_bit_identical(system.ray_trace(g["rays"][3], m_in, m_out), g["single"], "(8,) input")
+    parity.assert_bit_identical(system.ray_trace(g["pre"], m_in, m_out), g["ext"], "(K,N,8) input")
+    empty = system.ray_trace(np.zeros((0, 8)), m_in, m_out)
+    assert empty.shape == (7, 0, 8)
+
+
+@pytest.mark.parametrize("name", sorted(BIG))
+def test_big_batch_checksum(name, rt, rtm, checksums):
+    ref = checksums["big"][name]
+    system, m_in, m_out = systems.rebuild_system(ref["system"], rt, rtm)
+    hist = system.ray_trace(BIG[name](), m_in, m_out)
+    assert int(np.isnan(hist[-1, :, 0]).sum()) == ref["nan_rays_at_end"]
+    assert parity.digest(hist) == ref["sha256_history"]
+    last = system.ray_trace(BIG[name](), m_in, m_out, keep="last")
+    assert parity.digest(last[0]) == ref["sha256_last"]
+
+
+# ------------------------------------------------------------------------------------------------ vs the oracle
+def _fuzz_rays(n, seed, zlo=-8.0, spread=0.35):
+    rng = np.random.default_rng(seed)
+    rays = np.zeros((n, 8))
+    rays[:, 0:2] = rng.uniform(-14, 14, (n, 2))
+    rays[:, 2] = rng.uniform(zlo, zlo + 6, n)
+    d = rng.standard_normal((n, 3)) * np.array([spread, spread, 0.1]) + np.array([0, 0, 1.0])
+    rays[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 6] = rng.uniform(0, 100, n)
+    rays[:, 7] = rng.choice(np.array([0.405, 0.532, 0.785, 1.064]), size=n)
+    rays[rng.integers(0, n, n // 200)] = np.nan
+    rays[rng.integers(0, n, n // 200), 7] = np.nan
+    return rays
+
+
+def test_fuzz_edge_mix_vs_oracle(rt, rtm, oracle):
+    system, m_in, m_out, _ = systems.edge_mix(rt, rtm)
+    rays = _fuzz_rays(200_000, seed=3)
+    got = system.ray_trace(rays, m_in, m_out)
+    want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+    parity.assert_bit_identical(got, want, "edge_mix fuzz")
+    # a healthy mix of outcomes
+    dead = np.isnan(want[-1, :, 0]).mean()
+    assert 0.05 < dead < 0.98
+
+
+def test_fuzz_opm_vs_oracle(rt, rtm, oracle):
+    system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
+    rays = rt.get_ray_fan([1e-3, -2e-3, 5e-4], 1.05 * alpha1, 301, 532e-6, nphis=97)
+    got = system.ray_trace(rays, m_in, m_out)
+    want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+    parity.assert_bit_identical(got, want, "opm fan")
+
+
+def test_fuzz_mirrors_vs_oracle(rt, rtm, oracle):
+    system, m_in, m_out, _ = systems.mirrors(rt, rtm)
+    rays = _fuzz_rays(50_000, seed=9, zlo=-3.0, spread=0.25)
+    rays[:, 0:2] *= 0.2
+    got = system.ray_trace(rays, m_in, m_out)
+    want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+    parity.assert_bit_identical(got, want, "mirror fuzz")
+
+
+def test_keep_modes(rt, rtm, oracle):
+    system, m_in, m_out, rays = systems.relay10(rt, rtm)
+    full = oracle.ray_trace(system, rays, m_in, m_out)
+    parity.assert_bit_identical(system.ray_trace(rays, m_in, m_out, keep="last")[0], full[-1], "keep=last")
+    sel = system.ray_trace(rays, m_in, m_out, keep=[0, 9, -2, -1])
+    parity.assert_bit_identical(sel, full[[0, 9, 19, 20]], "keep=list")
+    with pytest.raises(ValueError):
+        system.ray_trace(rays, m_in, m_out, keep=[5, 4])
+    with pytest.raises(ValueError):
+        system.ray_trace(rays, m_in, m_out, keep=[99])
+
+
+def test_host_pipeline_many_chunks(rt, rtm, oracle):
+    """more rays than one staging chunk, pageable and pinned buffers, full history"""
+    from ray_trace_pb_b200 import _ffi, engine
+    system, m_in, m_out, _ = systems.plano_convex(rt, rtm)
+    rays = systems.lattice_rays(900, 26.0, -5.0, 0.5)            # 810,000 rays x 7 slabs: 3 chunks
+    want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+    got = system.ray_trace(rays, m_in, m_out)
+    parity.assert_bit_identical(got, want, "pageable")
+    pin_in = _ffi.pinned_empty(rays.shape)
+    pin_in[:] = rays
+    pin_out = _ffi.pinned_empty(want.shape)
+    materials = [m_in] + system.materials + [m_out]
+    engine.trace_host(system.surfaces, materials, pin_in, keep="all", out=pin_out)
+    parity.assert_bit_identical(pin_out, want, "pinned")
+    last = engine.trace_host(system.surfaces, materials, pin_in, keep="last")
+    parity.assert_bit_identical(last[0], want[-1], "pinned in, pageable out, last")
+
+
+def test_surface_propagate_operator(rt, rtm, oracle):
+    """Surface.propagate is the per-surface operator of the reference API (raytrace.py:1092)"""
+    system, m_in, m_out, rays = systems.edge_mix(rt, rtm)
+    mats = [m_in] + system.materials + [m_out]
+    cur = rays
+    for k, s in enumerate(system.surfaces):
+        cur = s.propagate(cur, mats[k], mats[k + 1])
+    want = oracle.ray_trace(system, rays, m_in, m_out)
+    parity.assert_bit_identical(cur, want, "chained propagate")
+
+
+# ------------------------------------------------------------------------------------------------ refractive indices
+def test_formula_mode_equals_table_mode(rt, rtm, torch, dev):
+    system = systems.relay10_system(rt, rtm)
+    mats = [rtm.Vacuum()] + system.materials + [rtm.Vacuum()]
+    rays = torch.from_numpy(systems.lattice_rays(300, 14.0, 0.0, 0.785, tilt=(0.003, 0.001))).cuda()
+    a = dev.trace_tensor(system.surfaces, mats, rays, keep="all", wavelengths="auto")
+    b = dev.trace_tensor(system.surfaces, mats, rays, keep="all", wavelengths=[0.785])
+    c = dev.trace_tensor(system.surfaces, mats, rays, keep="all", wavelengths=None)   # in-kernel Sellmeier
+    parity.assert_bit_identical(a.cpu().numpy(), b.cpu().numpy(), "auto vs given")
+    parity.assert_bit_identical(c.cpu().numpy(), b.cpu().numpy(), "in-kernel Sellmeier vs host table")
+
+
+def test_continuous_spectrum_uses_in_kernel_sellmeier(rt, rtm, oracle):
+    """one wavelength per ray (> RTB_MAX_WAVELENGTHS distinct values)"""
+    system = systems.relay10_system(rt, rtm)
+    rays = systems.lattice_rays(150, 12.0, 0.0, 0.785)
+    rays[:, 7] = np.linspace(0.45, 1.1, rays.shape[0])
+    rays[5, 7] = np.nan
+    got = system.ray_trace(rays, rtm.Vacuum(), rtm.Bk7())
+    want = oracle.ray_trace(system, rays, rtm.Vacuum(), rtm.Bk7(), n_threads=8)
+    parity.assert_bit_identical(got, want, "continuous spectrum")
+    # a medium that only exists as Python code cannot follow: loud refusal, no CPU fallback
+    cauchy = systems.make_cauchy(rtm)(1.5, 0.004)
+    with pytest.raises(NotImplementedError):
+        system.ray_trace(rays, rtm.Vacuum(), cauchy)
+
+
+def test_distinct_wavelengths_on_device(torch, dev):
+    rays = torch.zeros((100_000, 8), dtype=torch.float64, device="cuda")
+    wl = np.random.default_rng(0).choice([0.4, 0.5, 0.6, 0.7, np.nan], size=100_000)
+    rays[:, 7] = torch.from_numpy(wl).cuda()
+    assert dev.distinct_wavelengths_tensor(rays).tolist() == [0.4, 0.5, 0.6, 0.7]
+    rays[:, 7] = torch.arange(100_000, dtype=torch.float64, device="cuda")
+    assert dev.distinct_wavelengths_tensor(rays) is None
+    rays[:, 7] = float("nan")
+    assert dev.distinct_wavelengths_tensor(rays).size == 0
+
+
+# ------------------------------------------------------------------------------------------------ device API, sources
+def test_tensor_api_matches_host_api(rt, rtm, torch, dev):
+    system, m_in, m_out, rays = systems.opm(rt, rtm)
+    host = system.ray_trace(rays, m_in, m_out)
+    t = system.ray_trace(torch.from_numpy(rays).cuda(), m_in, m_out)
+    assert t.is_cuda and tuple(t.shape) == host.shape
+    parity.assert_bit_identical(t.cpu().numpy(), host, "tensor api")
+    with pytest.raises(TypeError):
+        dev.trace_tensor(system.surfaces, [m_in] + system.materials + [m_out], torch.zeros((4, 8), device="cuda"))
+
+
+@pytest.mark.parametrize("kind", ["fan", "collimated", "grid"])
+def test_sources_generate_and_fused_trace(kind, rt, rtm, oracle, dev):
+    system = systems.relay10_system(rt, rtm)
+    mats = [rtm.Vacuum()] + system.materials + [rtm.Vacuum()]
+    nrm = np.array([np.sin(0.01), 0, np.cos(0.01)])
+    nrm = nrm / np.linalg.norm(nrm)
+    if kind == "fan":
+        src = dev.RaySource.fan([0.3, -0.2, -150.0], 0.05, 201, 0.785, nphis=64)
+        ref = oracle.source_rays("fan", 201, 64, 0.05, [0.3, -0.2, -150.0], (0, 0, 1), 0.785)
+    elif kind == "collimated":
+        src = dev.RaySource.collimated([0, 0, 0], 12.0, 151, 0.785, nphis=90, phi_start=0.1, normal=nrm)
+        ref = oracle.source_rays("collimated", 151, 90, 12.0, [0, 0, 0], nrm, 0.785, b_start=0.1)
+    else:
+        src = dev.RaySource.grid([0, 0, 0], 12.0, 130, 0.785, half_width_v=9.0, n_v=110, normal=nrm)
+        ref = oracle.source_rays("grid", 130, 110, 12.0, [0, 0, 0], nrm, 0.785, b_max=9.0)
+    rays = src.generate()
+    got = rays.cpu().numpy()
+    assert got.shape == ref.shape
+    if kind == "grid":
+        parity.assert_bit_identical(got, ref, "grid source is libm-free, so exact")
+    else:
+        np.testing.assert_allclose(got, ref, rtol=0, atol=5e-16 * max(1.0, np.abs(ref[:, :6]).max()))
+    # slices of the index space
+    part = src.generate(first=1000, count=777).cpu().numpy()
+    parity.assert_bit_identical(part, got[1000:1777], "slice of the source")
+    # fused generate+trace == trace of the generated rays == oracle on those exact rays
+    fused = dev.trace_source(system.surfaces, mats, src, keep="all").cpu().numpy()
+    want = oracle.trace(system.surfaces, mats, got, keep_all=True, n_threads=8)
+    parity.assert_bit_identical(fused, want, "fused source trace vs oracle")
+    fused_part = dev.trace_source(system.surfaces, mats, src, first=1000, count=777, keep="last").cpu().numpy()
+    parity.assert_bit_identical(fused_part[0], want[-1, 1000:1777], "fused source slice")
+
+
+# ------------------------------------------------------------------------------------------------ reductions
+def test_fused_reductions(rt, rtm, oracle, dev, torch):
+    system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
+    mats = [m_in] + system.materials + [m_out]
+    rays = rt.get_ray_fan([1e-3, 1e-3, 1e-3 * np.tan(theta)], alpha1, 401, 532e-6, nphis=200)
+    hist = oracle.trace(system.surfaces, mats, rays, keep_all=True, n_threads=8)
+    slab = 2 * 8 + 2                                   # just after the O3 pupil flat
+    o3n = system.surfaces[8].normal
+    e2 = np.array([0.0, 1.0, 0.0])
+    e1 = np.cross(e2, o3n)
+    origin = system.surfaces[8].center
+    ok = ~np.isnan(hist[slab, :, 6])
+    phase_ref = float(np.mean(hist[slab, ok, 6]))
+    red = dev.Reducer(slab, origin=origin, e1=e1, e2=e2, grid_n=64, half_width=3.2, phase_ref=phase_ref)
+    out = dev.trace_tensor(system.surfaces, mats, torch.from_numpy(rays).cuda(), keep="last", reducer=red)
+    parity.assert_bit_identical(out[0].cpu().numpy(), hist[-1], "trace output unaffected by the reduction")
+    want_stats = oracle.reduce_stats(hist[slab], origin, e1, e2, phase_ref)
+    got_stats = red.stats_t.cpu().numpy()
+    assert got_stats[0] == want_stats[0] > 1000
+    np.testing.assert_allclose(got_stats[1:8], want_stats[1:8], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(got_stats[8:], want_stats[8:], rtol=1e-13)
+    want_grid = oracle.reduce_grid(hist[slab], origin, e1, e2, 64, 3.2, phase_ref)
+    got_grid = red.grid.cpu().numpy()
+    assert np.array_equal(got_grid[2], want_grid[2])
+    np.testing.assert_allclose(got_grid[:2], want_grid[:2], rtol=0, atol=1e-9 * max(1.0, want_grid[2].max()))
+    s = red.stats()
+    assert s["count"] == int(want_stats[0]) and s["rms_radius"] > 0
+    # accumulate across calls, keep="none" (reduction-only launch), then reset
+    dev.trace_tensor(system.surfaces, mats, torch.from_numpy(rays).cuda(), keep="none", reducer=red)
+    assert red.stats_t.cpu().numpy()[0] == 2 * want_stats[0]
+    red.reset()
+    assert red.stats_t.cpu().numpy()[0] == 0 and float(red.grid.abs().sum()) == 0.0
+
+
+def test_reduction_at_input_and_with_source(rt, rtm, oracle, dev):
+    system, m_in, m_out, _ = systems.plano_convex(rt, rtm)
+    mats = [m_in] + system.materials + [m_out]
+    src = dev.RaySource.grid([0, 0, -5.0], 20.0, 257, 0.5)
+    rays = src.generate().cpu().numpy()
+    hist = oracle.trace(system.surfaces, mats, rays, keep_all=True, n_threads=8)
+    for slab in (0, 3, 6):
+        red = dev.Reducer(slab, origin=(0, 0, 0), grid_n=32, half_width=21.0)
+        dev.trace_source(system.surfaces, mats, src, keep="none", reducer=red)
+        want = oracle.reduce_stats(hist[slab], (0, 0, 0), (1, 0, 0), (0, 1, 0))
+        got = red.stats_t.cpu().numpy()
+        assert got[0] == want[0]
+        np.testing.assert_allclose(got[1:8], want[1:8], rtol=1e-10, atol=1e-6)
+        assert np.array_equal(red.grid.cpu().numpy()[2], oracle.reduce_grid(hist[slab], (0, 0, 0), (1, 0, 0), (0, 1, 0), 32, 21.0)[2])
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def test_intersect_rays(rt, torch):
+    g = load_golden("intersect_rays")
+    parity.assert_bit_identical(rt.intersect_rays(g["r1"], g["r2"]), g["pts"], "pairs")
+    parity.assert_bit_identical(rt.intersect_rays(g["axis_ray"], g["others"]), g["pts_axis"], "broadcast")
+    parity.assert_bit_identical(rt.intersect_rays(g["a"], g["b"]), g["pts_deg"], "degenerate")
+    t = rt.intersect_rays(torch.from_numpy(g["r1"]).cuda(), torch.from_numpy(g["r2"]).cuda())
+    assert t.is_cuda
+    parity.assert_bit_identical(t.cpu().numpy(), g["pts"], "tensor in, tensor out")
+    with pytest.raises(ValueError):
+        rt.intersect_rays(g["r1"][:3], g["r2"][:4])
+
+
+def test_propagate_ray2plane_and_friends(rt, rtm, host_api):
+    g = load_golden("ray2plane")
+    out, ts = rt.propagate_ray2plane(g["rays"], np.array([0, 0.6, 0.8]), np.array([0, 0, 5.]), rtm.Bk7())
+    parity.assert_bit_identical(out, g["out"], "ray2plane rays")
+    parity.assert_bit_identical(ts, g["ts"], "ray2plane ts")
+    dists, near = rt.dist_pt2plane(np.array([[1., 2, 3], [0, 0, -1]]), np.array([0, 0.6, 0.8]), np.array([0, 0, 1.]))
+    np.testing.assert_allclose(dists, host_api["dist_pt2plane"]["dists"], rtol=1e-15)
+    np.testing.assert_allclose(near, host_api["dist_pt2plane"]["nearest"], rtol=1e-15, atol=1e-16)
+    # backward exclusion and per-ray centres
+    rays = g["rays"].copy()
+    centers = np.tile(np.array([0, 0, 5.0]), (len(rays), 1))
+    centers[::2, 2] = -5.0
+    out2, ts2 = rt.propagate_ray2plane(rays, np.array([0, 0, 1.0]), centers, rtm.Vacuum(), exclude_backward_propagation=True)
+    assert np.all(np.isnan(out2[::2])) and not np.any(np.isnan(out2[1::2])) and np.all(ts2[::2] < 0)
+
+
+def test_get_intersect_operator(rt, rtm, oracle):
+    system, m_in, m_out, rays = systems.edge_mix(rt, rtm)
+    # for forward-travelling rays get_intersect equals the at-surface slab of propagate
+    fwd = rays[np.nan_to_num(rays[:, 5]) > 0.2]
+    for s, m in ((system.surfaces[0], m_in), (system.surfaces[1], system.materials[0])):
+        at = s.get_intersect(fwd, m)
+        want = oracle.trace([s], [m, m], fwd, keep_all=True)[1]
+        parity.assert_bit_identical(at, want, type(s).__name__)
+    # a backwards ray is NOT culled by get_intersect of a sphere (only propagate applies the front-side test)
+    back = np.array([[0, 0, 40.0, 0, 0, -1.0, 0, 0.5]])
+    at = system.surfaces[1].get_intersect(back, m_in)
+    assert np.isfinite(at[0, 2]) and np.isnan(oracle.trace([system.surfaces[1]], [m_in, m_in], back)[1, 0, 2])
+
+
+def test_auto_focus_ray_modes(rt, rtm, host_api):
+    d = rt.Doublet(rtm.Nsk11(), rtm.Nsf19(), radius_crown=64.1, radius_flint=-183.685, radius_interface=-43.249,
+                   thickness_crown=3.5, thickness_flint=1.5, aperture_radius=10.)
+    for mode in ("ray-fan", "collimated"):
+        got = np.asarray(d.auto_focus(0.5876, rtm.Vacuum(), rtm.Vacuum(), mode=mode), dtype=float)
+        want = np.asarray(host_api["kidger_autofocus"][mode], dtype=float)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(got[~np.isnan(got)], want[~np.isnan(want)], rtol=1e-9)
+
+
+def test_launch_counter_and_probes():
+    import ctypes
+    from ray_trace_pb_b200 import _ffi
+    L = _ffi.lib()
+    before = L.rtb_launch_count()
+    rate = ctypes.c_double()
+    ms = ctypes.c_double()
+    _ffi.check(L.rtb_measure_dfma_rate(0, ctypes.byref(rate), ctypes.byref(ms)))
+    assert 1e12 < rate.value < 1e14, rate.value          # B200: ~1.9e13 DFMA/s nominal
+    bw = ctypes.c_double()
+    _ffi.check(L.rtb_measure_copy_bandwidth(0, 1 << 30, ctypes.byref(bw)))
+    assert 1e12 < bw.value < 1.2e13, bw.value
+    assert L.rtb_launch_count() >= before
