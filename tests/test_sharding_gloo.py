@@ -84,7 +84,8 @@ def test_two_rank_gloo_allreduce_matches_single_process(tmp_path, rt, rtm, oracl
     want_stats = oracle.reduce_stats(last, (0, 0, 0), (1, 0, 0), (0, 1, 0))
     want_grid = oracle.reduce_grid(last, (0, 0, 0), (1, 0, 0), (0, 1, 0), 32, 21.0)
     assert parts[0]["stats"][0] == want_stats[0]
-    np.testing.assert_allclose(parts[0]["stats"], want_stats, rtol=1e-12)
+    # sums over a symmetric bundle cancel to ~0, so compare against the scale of the summands (|u| <= 20, N ~ 9e3)
+    np.testing.assert_allclose(parts[0]["stats"], want_stats, rtol=1e-12, atol=1e-9)
     assert np.array_equal(parts[0]["grid"][2], want_grid[2])
     np.testing.assert_allclose(parts[0]["grid"], want_grid, rtol=0, atol=1e-9)
 
