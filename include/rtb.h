@@ -32,7 +32,7 @@ extern "C" {
 
 #define RTB_ABI_VERSION 1
 #define RTB_MAX_SURFACES 64
-#define RTB_MAX_WAVELENGTHS 16 /* rows of the host refractive-index table (one extra row answers NaN wavelengths) */
+#define RTB_MAX_WAVELENGTHS 8 /* rows of the host refractive-index table (one extra row answers NaN wavelengths) */
 #define RTB_MAX_KEEP (2 * RTB_MAX_SURFACES + 1)
 
 typedef enum rtb_status {
@@ -265,6 +265,13 @@ int rtb_distinct_wavelengths_device(const double *rays_dev, int64_t n_rays, doub
 /* page-locked host memory for zero-staging transfers in rtb_trace_host (NULL on failure) */
 void *rtb_host_alloc(size_t bytes);
 void rtb_host_free(void *p);
+
+/*
+ * Self-test of the library's factored IEEE division / square root (csrc/exact_math.cuh) against the built-in
+ * operators on n_cases pseudo-random operand sets (raw bit patterns, moderate magnitudes, special values).
+ * mismatches[0] = scalar divisions, [1] = three-way divisions, [2] = square roots that differ in any bit.
+ */
+int rtb_selftest_exact_math(int device, uint64_t seed, int64_t n_cases, uint64_t mismatches[3]);
 
 /* ---- measurement helpers ------------------------------------------------------------------------------------ */
 /*

@@ -13,11 +13,14 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "_lib" / "librtb.so"
+import os
+
+# RTB_LIBRARY_PATH selects another build of the same library (used to A/B kernel variants on the GPU box)
+LIB_PATH = Path(os.environ.get("RTB_LIBRARY_PATH") or (Path(__file__).resolve().parent / "_lib" / "librtb.so"))
 
 RTB_ABI_VERSION = 1
 RTB_MAX_SURFACES = 64
-RTB_MAX_WAVELENGTHS = 16
+RTB_MAX_WAVELENGTHS = 8
 RTB_N_STATS = 12
 
 RTB_OK = 0
@@ -81,7 +84,8 @@ _lib = None
 EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_count", "rtb_trace_device",
            "rtb_trace_host", "rtb_trace_source", "rtb_generate_device", "rtb_reduce_init",
            "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
-           "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_host_alloc", "rtb_host_free"]
+           "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_host_alloc", "rtb_host_free",
+           "rtb_selftest_exact_math"]
 
 
 def lib():
@@ -107,6 +111,8 @@ def lib():
     L.rtb_intersect_rays_device.argtypes = [vp, i64, vp, i64, vp, i32, vp]
     L.rtb_ray2plane_device.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, vp, vp, i32, vp]
     L.rtb_distinct_wavelengths_device.argtypes = [vp, i64, vp, dp, C.POINTER(C.c_int32), i32, vp]
+    L.rtb_selftest_exact_math.argtypes = [i32, C.c_uint64, i64, C.POINTER(C.c_uint64)]
+    L.rtb_selftest_exact_math.restype = i32
     L.rtb_measure_dfma_rate.argtypes = [i32, dp, dp]
     L.rtb_measure_copy_bandwidth.argtypes = [i32, i64, dp]
     L.rtb_host_alloc.argtypes = [C.c_size_t]

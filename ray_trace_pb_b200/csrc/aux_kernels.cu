@@ -4,6 +4,7 @@
 #include <cmath>
 #include <math_constants.h>
 
+#include "exact_math.cuh"
 #include "rtb_device.cuh"
 
 namespace rtb {
@@ -195,6 +196,60 @@ __global__ void fill_u64_kernel(unsigned long long *p, int n, unsigned long long
     if (i < n) p[i] = v;
 }
 
+// ---- self-test of exact_math.cuh against the built-in IEEE operators ------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ double test_operand(unsigned long long h, int category)
+{
+    const double specials[16] = {0.0, -0.0, 1.0, -1.0, CUDART_INF, -CUDART_INF, CUDART_NAN, 4.9406564584124654e-324,
+                                 2.2250738585072014e-308, 1.7976931348623157e308, 1e-300, 1e300, 0.5, 3.0,
+                                 1.0000000000000002, 6.283185307179586};
+    if (category == 0) return __longlong_as_double((long long)h);                 // raw bits: every class of double
+    if (category == 2) return specials[h & 15];
+    // moderate magnitudes: random mantissa and sign, exponent within 2^-40 .. 2^40 (category 1) or 2^-3..2^3 (3)
+    const int span = (category == 1) ? 81 : 7;
+    const unsigned long long expo = 1023ull - span / 2 + (h >> 52) % span;
+    return __longlong_as_double((long long)((h & 0x800FFFFFFFFFFFFFull) | (expo << 52)));
+}
+
+__device__ __forceinline__ bool same_bits(double a, double b)
+{
+    return (a != a && b != b) || (__double_as_longlong(a) == __double_as_longlong(b));
+}
+
+__global__ void __launch_bounds__(256) exact_math_selftest_kernel(unsigned long long seed, long long n,
+                                                                  unsigned long long *bad)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long bad_div = 0, bad_div3 = 0, bad_sqrt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int cat = (int)(i & 3);
+        const unsigned long long h0 = splitmix64(seed ^ (unsigned long long)(4 * i));
+        const double b = test_operand(splitmix64(h0), cat);
+        double a0 = test_operand(splitmix64(h0 + 1), cat);
+        double a1 = test_operand(splitmix64(h0 + 2), cat == 3 ? 2 : cat);       // zeros next to ordinary numbers
+        double a2 = test_operand(splitmix64(h0 + 3), cat);
+        if (cat == 3 && (h0 & 8)) a2 = b * 1.0000000000000002;                   // quotients next to 1
+        bad_div += !same_bits(xm::div(a0, b), a0 / b);
+        const xm::Rcp r = xm::make_rcp(b);
+        bad_div += !same_bits(xm::div(a1, r), a1 / b);
+        double x = a0, y = a1, z = a2;
+        xm::div3(x, y, z, r);
+        bad_div3 += !(same_bits(x, a0 / b) && same_bits(y, a1 / b) && same_bits(z, a2 / b));
+        bad_sqrt += !same_bits(xm::sqrt(a0), sqrt(a0));
+        bad_sqrt += !same_bits(xm::sqrt(fabs(a2)), sqrt(fabs(a2)));
+    }
+    if (bad_div) atomicAdd(bad + 0, bad_div);
+    if (bad_div3) atomicAdd(bad + 1, bad_div3);
+    if (bad_sqrt) atomicAdd(bad + 2, bad_sqrt);
+}
+
 // Register-only DFMA throughput: 8 independent chains per thread, explicit fused multiply-adds.
 __global__ void __launch_bounds__(256) dfma_probe_kernel(double *sink, int iters, double seed)
 {
@@ -276,6 +331,18 @@ cudaError_t run_distinct_wavelengths(const double *rays, long long n, double *ta
         if (host[k] != kEmptySlot) host_out[count++] = __builtin_bit_cast(double, host[k]);
     *n_found = count;
     return cudaGetLastError();
+}
+
+cudaError_t run_exact_math_selftest(unsigned long long seed, long long n, unsigned long long *bad_host, int sm_count)
+{
+    unsigned long long *bad = nullptr;
+    cudaError_t e = cudaMalloc(&bad, 3 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    cudaMemset(bad, 0, 3 * sizeof(unsigned long long));
+    exact_math_selftest_kernel<<<sm_count * 8, 256>>>(seed, n, bad);
+    e = cudaMemcpy(bad_host, bad, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(bad);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t run_dfma_probe(int sm_count, double *dfma_per_s, double *elapsed_ms)

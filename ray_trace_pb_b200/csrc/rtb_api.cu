@@ -23,6 +23,7 @@ cudaError_t launch_ray2plane(const double *rays, long long n, const double *norm
                              double *out, double *ts, cudaStream_t stream);
 cudaError_t run_distinct_wavelengths(const double *rays, long long n, double *table_dev, int capacity,
                                      double *host_out, int *n_found, int sm_count, cudaStream_t stream);
+cudaError_t run_exact_math_selftest(unsigned long long seed, long long n, unsigned long long *bad_host, int sm_count);
 cudaError_t run_dfma_probe(int sm_count, double *dfma_per_s, double *elapsed_ms);
 cudaError_t run_copy_probe(long long bytes, double *bytes_per_s);
 } // namespace rtb
@@ -109,6 +110,56 @@ struct DeviceGuard {
     }
 };
 
+// ---- exact squared-domain thresholds (see DevSurface in rtb_device.cuh) ------------------------------------------
+// fl(sqrt(.)) is monotone, so  fl(sqrt(s)) <= r  <=>  s <= sq_upper(r)  and  fl(sqrt(s)) >= r  <=>  s >= sq_lower(r).
+double sq_upper(double r) // largest s with fl(sqrt(s)) <= r
+{
+    if (std::isnan(r)) return r;
+    if (r < 0) return -1.0;
+    if (std::isinf(r)) return r;
+    double c = r * r;
+    while (std::sqrt(c) > r) c = std::nextafter(c, -INFINITY);
+    for (;;) {
+        const double n = std::nextafter(c, INFINITY);
+        if (std::isinf(n) || !(std::sqrt(n) <= r)) break;
+        c = n;
+    }
+    return c;
+}
+
+double sq_lower(double r) // smallest s >= 0 with fl(sqrt(s)) >= r
+{
+    if (std::isnan(r)) return r;
+    if (r <= 0) return 0.0;
+    if (std::isinf(r)) return r;
+    double c = r * r;
+    while (std::sqrt(c) < r) c = std::nextafter(c, INFINITY);
+    for (;;) {
+        const double n = std::nextafter(c, -INFINITY);
+        if (n < 0 || !(std::sqrt(n) >= r)) break;
+        c = n;
+    }
+    return c;
+}
+
+// | fl(norm - abs_radius) | < tol   <=>   lo <= norm <= hi   (fl(x - a) is monotone in x)
+void on_sphere_window(double abs_radius, double tol, double &lo, double &hi)
+{
+    if (!std::isfinite(abs_radius)) {
+        lo = INFINITY;
+        hi = -INFINITY;
+        return;
+    }
+    double r = abs_radius - tol;
+    while (!((r - abs_radius) > -tol)) r = std::nextafter(r, INFINITY);
+    while ((std::nextafter(r, -INFINITY) - abs_radius) > -tol) r = std::nextafter(r, -INFINITY);
+    lo = r;
+    r = abs_radius + tol;
+    while (!((r - abs_radius) < tol)) r = std::nextafter(r, -INFINITY);
+    while ((std::nextafter(r, INFINITY) - abs_radius) < tol) r = std::nextafter(r, INFINITY);
+    hi = r;
+}
+
 // ---- packing ------------------------------------------------------------------------------------------------
 int n_out_slabs(const rtb_system *sys, const rtb_trace_opts *opts)
 {
@@ -150,6 +201,11 @@ int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TracePar
         d.focal_len = a.focal_len;
         d.nfx = a.normal_f[0]; d.nfy = a.normal_f[1]; d.nfz = a.normal_f[2];
         d.sin_alpha = a.sin_alpha;
+        d.ap_sq_max = sq_upper(a.aperture_rad);
+        double lo, hi;
+        on_sphere_window(a.abs_radius, 1e-12, lo, hi);
+        d.on_sq_lo = sq_lower(lo);
+        d.on_sq_hi = sq_upper(hi);
     }
     for (int k = 0; k <= S; k++) {
         const rtb_material &a = sys->materials[k];
@@ -166,8 +222,13 @@ int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TracePar
         d.n_const = a.n_const;
     }
     for (int k = 0; k < sys->n_wavelengths; k++) P.wl[k] = sys->wavelengths[k];
-    if (sys->n_wavelengths > 0)
+    if (sys->n_wavelengths > 0) {
         memcpy(P.n_tab, sys->n_table, sizeof(double) * (size_t)(sys->n_wavelengths + 1) * (size_t)(S + 1));
+        // n1 / n2 per (wavelength row, surface): the host's IEEE division gives the bits the kernel's would
+        for (int r = 0; r <= sys->n_wavelengths; r++)
+            for (int k = 0; k < S; k++)
+                P.ratio_tab[r * (S + 1) + k] = P.n_tab[r * (S + 1) + k] / P.n_tab[r * (S + 1) + k + 1];
+    }
 
     // which slabs go where
     const int n_slabs = 2 * S + 1;
@@ -564,6 +625,22 @@ int rtb_distinct_wavelengths_device(const double *rays_dev, int64_t n_rays, doub
     std::sort(vals, vals + found);
     for (int k = 0; k < found; k++) wavelengths_host[k] = vals[k];
     *n_found = found;
+    return RTB_OK;
+}
+
+int rtb_selftest_exact_math(int device, uint64_t seed, int64_t n_cases, uint64_t mismatches[3])
+{
+    if (!mismatches || n_cases < 0) return fail(RTB_ERR_INVALID, "bad arguments");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    unsigned long long bad[3] = {0, 0, 0};
+    cudaError_t e = rtb::run_exact_math_selftest(seed, n_cases, bad, ctx->sm_count);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "exact-math self-test failed to run: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    for (int k = 0; k < 3; k++) mismatches[k] = bad[k];
     return RTB_OK;
 }
 

@@ -22,6 +22,13 @@ constexpr int kMaxMedia = RTB_MAX_SURFACES + 1;
 constexpr int kMaxWavelengths = RTB_MAX_WAVELENGTHS;
 constexpr int kMaxSlabs = 2 * RTB_MAX_SURFACES + 1;
 
+// launch shape of the trace kernels: 128-thread blocks, register budget for kTraceMinBlocks resident blocks per SM
+constexpr int kTraceThreads = 128;
+#ifndef RTB_TRACE_MIN_BLOCKS
+#define RTB_TRACE_MIN_BLOCKS 4
+#endif
+constexpr int kTraceMinBlocks = RTB_TRACE_MIN_BLOCKS;
+
 struct DevSurface {
     double cx, cy, cz;    // center
     double nx, ny, nz;    // geometric normal (flat / mirror / lens)
@@ -31,6 +38,12 @@ struct DevSurface {
     double focal_len;
     double nfx, nfy, nfz; // normal * focal_len
     double sin_alpha;
+    // exact squared-domain thresholds, computed on the host (rtb_api.cu: pack_thresholds) so that the kernel can
+    // test  norm <= aperture  and  | norm - |R| | < 1e-12  without taking the square root:
+    //   in_aperture  <=>  s <= ap_sq_max          (s = the left-associated sum of squares the reference feeds to sqrt)
+    //   on_sphere    <=>  on_sq_lo <= s <= on_sq_hi
+    double ap_sq_max;
+    double on_sq_lo, on_sq_hi;
     int32_t kind;
     int32_t pad;
 };
@@ -89,6 +102,7 @@ struct TraceParams {
     DevMaterial mat[kMaxMedia];
     double wl[kMaxWavelengths];
     double n_tab[(kMaxWavelengths + 1) * kMaxMedia]; // row-major [wavelength row][medium], row n_wl = NaN answer
+    double ratio_tab[(kMaxWavelengths + 1) * kMaxMedia]; // [row][k] = n_tab[row][k] / n_tab[row][k+1] (host IEEE division)
 };
 
 static_assert(sizeof(TraceParams) < 32764, "TraceParams must fit the kernel parameter space");

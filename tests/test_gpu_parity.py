@@ -333,6 +333,16 @@ def test_auto_focus_ray_modes(rt, rtm, host_api):
         np.testing.assert_allclose(got[~np.isnan(got)], want[~np.isnan(want)], rtol=1e-9)
 
 
+def test_exact_math_selftest():
+    """csrc/exact_math.cuh (factored IEEE division / sqrt) against the built-in operators: no bit may differ"""
+    import ctypes
+    from ray_trace_pb_b200 import _ffi
+    bad = (ctypes.c_uint64 * 3)()
+    for seed in (1, 0xDEADBEEF):
+        _ffi.check(_ffi.lib().rtb_selftest_exact_math(0, seed, 200_000_000, bad))
+        assert list(bad) == [0, 0, 0], f"mismatches (div, div3, sqrt) = {list(bad)} for seed {seed}"
+
+
 def test_launch_counter_and_probes():
     import ctypes
     from ray_trace_pb_b200 import _ffi

@@ -1,0 +1,37 @@
+"""Small driver for ncu: a few launches of the fused trace on the bench workload (no reduction, final slab)."""
+import argparse
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from ray_trace_pb_b200 import device as dev  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rays", type=float, default=2e7)
+ap.add_argument("--launches", type=int, default=4)
+ap.add_argument("--keep", default="last")
+ap.add_argument("--reduce", default="none")
+args = ap.parse_args()
+
+system, materials = bench.relay_system()
+source, side = bench.beam_source(int(args.rays))
+rays = source.generate()
+reducer = None
+if args.reduce != "none":
+    reducer = dev.Reducer(12, origin=(8.0, 0, 0), grid_n=2048 if args.reduce == "grid" else 0, half_width=8.0)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.launches + 1)]
+ev[0].record()
+for i in range(args.launches):
+    out = dev.trace_tensor(system.surfaces, materials, rays, keep=args.keep, wavelengths=[bench.WAVELENGTH],
+                           reducer=reducer)
+    ev[i + 1].record()
+torch.cuda.synchronize()
+ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.launches)]
+n = rays.shape[0]
+print(f"rays {n}  ms/launch {['%.3f' % m for m in ms]}  best {n * 10 / min(ms) / 1e-3 / 1e9:.2f} G ray*surf/s")
