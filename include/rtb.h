@@ -99,8 +99,11 @@ typedef struct rtb_material {
  * Refractive indices come from one of two places:
  *   n_wavelengths > 0 : `wavelengths[n_wavelengths]` lists every distinct wavelength bit pattern of the batch and
  *        `n_table[(n_wavelengths + 1) * (S + 1)]` (row-major, row = wavelength, column = medium) holds material.n()
- *        evaluated on the host by the user's own Python objects; the extra last row is the answer for a NaN (or
- *        unlisted) wavelength.  Works for every material kind, bit exact by construction.
+ *        evaluated on the host by the user's own Python objects; the extra last row is the answer for a NaN
+ *        wavelength.  Works for every material kind, bit exact by construction.  A ray whose (valid) wavelength
+ *        is not listed is evaluated in the kernel like the n_wavelengths == 0 case, so the list may be a sample
+ *        of the batch UNLESS a RTB_MAT_TABLE_ONLY medium is present (then it must be complete: such a ray's
+ *        index would be NaN).
  *   n_wavelengths == 0: the kernel evaluates Constant / Sellmeier media per ray; RTB_MAT_TABLE_ONLY media are
  *        then refused with RTB_ERR_UNSUPPORTED.
  */
@@ -261,6 +264,9 @@ int rtb_ray2plane_device(const double *rays_dev, int64_t n_rays, const double *n
  */
 int rtb_distinct_wavelengths_device(const double *rays_dev, int64_t n_rays, double *table_dev,
                                     double *wavelengths_host, int32_t *n_found, int device, void *stream);
+
+/* The same for a host batch (multi-threaded scan of column 7); wavelengths_out holds RTB_MAX_WAVELENGTHS + 1 doubles. */
+int rtb_distinct_wavelengths_host(const double *rays_host, int64_t n_rays, double *wavelengths_out, int32_t *n_found);
 
 /* page-locked host memory for zero-staging transfers in rtb_trace_host (NULL on failure) */
 void *rtb_host_alloc(size_t bytes);

@@ -84,7 +84,7 @@ _lib = None
 EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_count", "rtb_trace_device",
            "rtb_trace_host", "rtb_trace_source", "rtb_generate_device", "rtb_reduce_init",
            "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
-           "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_host_alloc", "rtb_host_free",
+           "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
            "rtb_selftest_exact_math"]
 
 
@@ -111,6 +111,8 @@ def lib():
     L.rtb_intersect_rays_device.argtypes = [vp, i64, vp, i64, vp, i32, vp]
     L.rtb_ray2plane_device.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, vp, vp, i32, vp]
     L.rtb_distinct_wavelengths_device.argtypes = [vp, i64, vp, dp, C.POINTER(C.c_int32), i32, vp]
+    L.rtb_distinct_wavelengths_host.argtypes = [vp, i64, dp, C.POINTER(C.c_int32)]
+    L.rtb_distinct_wavelengths_host.restype = i32
     L.rtb_selftest_exact_math.argtypes = [i32, C.c_uint64, i64, C.POINTER(C.c_uint64)]
     L.rtb_selftest_exact_math.restype = i32
     L.rtb_measure_dfma_rate.argtypes = [i32, dp, dp]

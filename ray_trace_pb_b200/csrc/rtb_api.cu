@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "rtb_device.cuh"
@@ -201,6 +202,12 @@ int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TracePar
         d.focal_len = a.focal_len;
         d.nfx = a.normal_f[0]; d.nfy = a.normal_f[1]; d.nfz = a.normal_f[2];
         d.sin_alpha = a.sin_alpha;
+        auto z_aligned = [](const double v[3]) -> int8_t {
+            if (v[0] == 0.0 && v[1] == 0.0 && (v[2] == 1.0 || v[2] == -1.0)) return v[2] > 0 ? 1 : -1;
+            return 0;
+        };
+        d.z_normal = z_aligned(a.normal);
+        d.z_axis = z_aligned(a.input_axis);
         d.ap_sq_max = sq_upper(a.aperture_rad);
         double lo, hi;
         on_sphere_window(a.abs_radius, 1e-12, lo, hi);
@@ -625,6 +632,56 @@ int rtb_distinct_wavelengths_device(const double *rays_dev, int64_t n_rays, doub
     std::sort(vals, vals + found);
     for (int k = 0; k < found; k++) wavelengths_host[k] = vals[k];
     *n_found = found;
+    return RTB_OK;
+}
+
+int rtb_distinct_wavelengths_host(const double *rays_host, int64_t n_rays, double *wavelengths_out, int32_t *n_found)
+{
+    if (n_rays < 0 || !wavelengths_out || !n_found) return fail(RTB_ERR_INVALID, "bad arguments");
+    if (n_rays > 0 && !rays_host) return fail(RTB_ERR_INVALID, "rays_host is NULL");
+    constexpr int cap = RTB_MAX_WAVELENGTHS + 1;
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_threads = (int)std::min<int64_t>(std::max(1u, std::min(hw, 16u)), std::max<int64_t>(1, n_rays / 65536));
+    struct Local {
+        uint64_t v[cap];
+        int n = 0;
+    };
+    std::vector<Local> found(n_threads);
+    auto scan = [&](int t) {
+        Local &L = found[t];
+        const int64_t lo = n_rays * t / n_threads, hi = n_rays * (t + 1) / n_threads;
+        uint64_t last = 0;
+        bool have_last = false;
+        for (int64_t i = lo; i < hi && L.n < cap; i++) {
+            const double w = rays_host[8 * i + 7];
+            if (w != w) continue;
+            uint64_t bits;
+            memcpy(&bits, &w, 8);
+            if (have_last && bits == last) continue;
+            last = bits;
+            have_last = true;
+            int k = 0;
+            while (k < L.n && L.v[k] != bits) k++;
+            if (k == L.n) L.v[L.n++] = bits;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(scan, t);
+    scan(0);
+    for (auto &th : pool) th.join();
+    uint64_t all[cap];
+    int n = 0;
+    for (int t = 0; t < n_threads && n < cap; t++)
+        for (int k = 0; k < found[t].n && n < cap; k++) {
+            int j = 0;
+            while (j < n && all[j] != found[t].v[k]) j++;
+            if (j == n) all[n++] = found[t].v[k];
+        }
+    double vals[cap];
+    for (int k = 0; k < n; k++) memcpy(&vals[k], &all[k], 8);
+    std::sort(vals, vals + n);
+    for (int k = 0; k < n; k++) wavelengths_out[k] = vals[k];
+    *n_found = n;
     return RTB_OK;
 }
 

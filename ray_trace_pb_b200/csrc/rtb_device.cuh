@@ -25,7 +25,7 @@ constexpr int kMaxSlabs = 2 * RTB_MAX_SURFACES + 1;
 // launch shape of the trace kernels: 128-thread blocks, register budget for kTraceMinBlocks resident blocks per SM
 constexpr int kTraceThreads = 128;
 #ifndef RTB_TRACE_MIN_BLOCKS
-#define RTB_TRACE_MIN_BLOCKS 4
+#define RTB_TRACE_MIN_BLOCKS 6
 #endif
 constexpr int kTraceMinBlocks = RTB_TRACE_MIN_BLOCKS;
 
@@ -45,7 +45,9 @@ struct DevSurface {
     double ap_sq_max;
     double on_sq_lo, on_sq_hi;
     int32_t kind;
-    int32_t pad;
+    int8_t z_normal; // +-1 when normal == (0, 0, +-1) exactly, else 0   (shortcuts of the Optimistic policy)
+    int8_t z_axis;   // +-1 when input_axis == (0, 0, +-1) exactly, else 0
+    int16_t pad;
 };
 
 struct DevMaterial {

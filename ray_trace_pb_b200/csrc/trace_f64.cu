@@ -37,10 +37,14 @@ struct SharedConsts {
 __device__ __forceinline__ double eval_index(const DevMaterial &m, double wl)
 {
     if (m.kind == RTB_MAT_CONSTANT) return m.n_const;
+    if (m.kind == RTB_MAT_TABLE_ONLY) return nan64(); // only the host knows this medium
     const double w2 = wl * wl;
     const double acc = (xm::div(m.b0 * w2, w2 - m.c0) + xm::div(m.b1 * w2, w2 - m.c1)) + xm::div(m.b2 * w2, w2 - m.c2);
     return xm::sqrt(acc + 1.0);
 }
+
+// a ray whose wavelength is not in the host table (the table may be built from a sample of the batch)
+static __device__ __noinline__ double index_for_unlisted(const DevMaterial *m, double wl) { return eval_index(*m, wl); }
 
 // ---- ray I/O ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_ray(const double *base, long long i, Ray &r)
@@ -264,12 +268,15 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
         const double wl0 = cur.wl;
         const xm::Rcp rcp_wl = xm::make_rcp(wl0);
         int row = 0;
+        bool unlisted = false;
         if (USE_TABLE) {
-            row = P.n_wl; // NaN / unlisted wavelength row
+            row = P.n_wl; // the NaN-wavelength row
             const long long bits = __double_as_longlong(wl0);
 #pragma unroll 1
             for (int k = 0; k < P.n_wl; k++)
                 if (__double_as_longlong(P.wl[k]) == bits) row = k;
+            // a valid wavelength the table does not list: evaluate Sellmeier / constant media for this ray
+            unlisted = (row == P.n_wl) && (wl0 == wl0);
             row *= n_med;
         }
         if (GENERAL) {
@@ -277,13 +284,18 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             if (reducing && P.red.slab == 0) reduce_sample(P.red, cur, tally);
         }
 
-        double n1 = USE_TABLE ? s_ntab[row] : eval_index(P.mat[0], wl0);
+        double n1 = !USE_TABLE ? eval_index(P.mat[0], wl0)
+                               : (unlisted ? index_for_unlisted(&P.mat[0], wl0) : s_ntab[row]);
         bool dead = false;
 #pragma unroll 1
         for (int k = 0; k < P.n_surf; k++) {
             const DevSurface &s = P.surf[k];
-            const double n2 = USE_TABLE ? s_ntab[row + k + 1] : eval_index(P.mat[k + 1], wl0);
+            const double n2 = !USE_TABLE ? eval_index(P.mat[k + 1], wl0)
+                                         : (unlisted ? index_for_unlisted(&P.mat[k + 1], wl0) : s_ntab[row + k + 1]);
             Ray at, after;
+            const int pa = GENERAL ? P.slab_pos[2 * k + 1] : -1, pb = GENERAL ? P.slab_pos[2 * k + 2] : -1;
+            const bool reduce_at = reducing && P.red.slab == 2 * k + 1;
+            const bool need_at = GENERAL && (pa >= 0 || reduce_at);
             if (dead) {
                 // an all-NaN ray stays all-NaN through every kind of surface: skip the arithmetic
                 set_nan(at);
@@ -297,15 +309,15 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                 // paths' domain, otherwise redo this surface with the Careful arithmetic (surface_steps.cuh)
                 Optimistic m;
                 if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {
-                    const double ratio = USE_TABLE ? s_ratio[row + k] : xm::div(n1, n2);
-                    dead = refracting_step<Optimistic, GENERAL>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only,
-                                                                at, after);
+                    const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + k] : xm::div(n1, n2);
+                    dead = refracting_step<Optimistic>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only, need_at,
+                                                       at, after);
                     if (!m.ok) {
                         const StepResult r = careful_refracting(&s, cur, n1, ratio, !intersect_only);
                         at = r.at; after = r.after; dead = r.dead;
                     }
                 } else if (s.kind == RTB_SURF_MIRROR) {
-                    dead = mirror_step<Optimistic, GENERAL>(m, s, cur, n1, rcp_wl, at, after);
+                    dead = mirror_step<Optimistic>(m, s, cur, n1, rcp_wl, need_at, at, after);
                     if (!m.ok) {
                         const StepResult r = careful_mirror(&s, cur, n1);
                         at = r.at; after = r.after; dead = r.dead;
@@ -319,13 +331,10 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                 }
             }
             if (GENERAL) {
-                const int pa = P.slab_pos[2 * k + 1], pb = P.slab_pos[2 * k + 2];
                 if (pa >= 0) store_ray(P.out + pa * P.out_stride, i, at);
                 if (pb >= 0) store_ray(P.out + pb * P.out_stride, i, after);
-                if (reducing) {
-                    if (P.red.slab == 2 * k + 1) reduce_sample(P.red, at, tally);
-                    if (P.red.slab == 2 * k + 2) reduce_sample(P.red, after, tally);
-                }
+                if (reduce_at) reduce_sample(P.red, at, tally);
+                if (reducing && P.red.slab == 2 * k + 2) reduce_sample(P.red, after, tally);
             }
             cur = after;
             n1 = n2;

@@ -354,7 +354,8 @@ def propagate_ray2plane(rays, normal, center, material, exclude_backward_propaga
 def surface_intersect(surface, rays, material, device: int = 0):
     """Surface.get_intersect (raytrace.py:1331-1337, 1398-1403, 1479-1516, 1580-1584) as a one-surface device trace."""
     rays = np.atleast_2d(np.asarray(rays, dtype=np.float64))
-    uniq = engine.choose_wavelength_table([material, material], rays[:, 7])
+    rays = np.ascontiguousarray(rays)
+    uniq = engine.choose_wavelength_table([material, material], rays)
     packed = engine.pack_system([surface], [material, material], uniq)
     mode, idx, n_out = engine.resolve_keep([1], packed.n_slabs)
     opts = engine.make_opts(mode, idx, "f64")

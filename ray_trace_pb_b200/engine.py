@@ -191,12 +191,40 @@ def make_opts(keep_mode, keep_idx, precision="f64", reduce=None):
 # ----------------------------------------------------------------------------------------------------------
 # host-buffer trace (the drop-in call)
 # ----------------------------------------------------------------------------------------------------------
-def choose_wavelength_table(materials, wl_column: np.ndarray):
-    """Distinct wavelengths for the host table, or None when the kernel should evaluate n() itself."""
-    uniq = distinct_wavelengths(wl_column, _ffi.RTB_MAX_WAVELENGTHS)
-    if uniq is not None and uniq.size == 0:
-        uniq = None if all(pack_material(m).kind != KIND_TABLE_ONLY for m in materials) else np.array([1.0])
-    return uniq
+def distinct_wavelengths_scan(rays: np.ndarray):
+    """Complete list of distinct non-NaN wavelengths of a contiguous (N, 8) host batch (threaded C scan), or None
+    when there are more than RTB_MAX_WAVELENGTHS."""
+    out = np.empty(_ffi.RTB_MAX_WAVELENGTHS + 1, dtype=np.float64)
+    found = C.c_int32(0)
+    _ffi.check(_ffi.lib().rtb_distinct_wavelengths_host(rays.ctypes.data, rays.shape[0],
+                                                        out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(found)))
+    if found.value > _ffi.RTB_MAX_WAVELENGTHS:
+        return None
+    return out[:found.value].copy()
+
+
+def choose_wavelength_table(materials, rays: np.ndarray):
+    """
+    Wavelengths to tabulate on the host for a contiguous (N, 8) host batch, or None for "evaluate in the kernel".
+
+    * A medium that only exists as Python code (``Ebaf11``, user subclasses) needs the COMPLETE list: full scan.
+    * Otherwise the kernel can evaluate any wavelength the table misses, so a 64-ray sample is enough to catch the
+      usual "a few spectral lines per batch" case without reading the whole column on the host.
+    """
+    n = rays.shape[0]
+    table_only = any(pack_material(m).kind == KIND_TABLE_ONLY for m in materials)
+    if table_only:
+        uniq = distinct_wavelengths_scan(rays)
+        if uniq is None:
+            return None          # pack_system raises the NotImplementedError naming the media
+        return uniq if uniq.size else np.array([1.0])   # no valid wavelength at all: only the NaN row is used
+    if n == 0:
+        return None
+    sample = rays[np.linspace(0, n - 1, num=min(n, 64)).astype(np.int64), 7]
+    uniq = distinct_wavelengths(sample, _ffi.RTB_MAX_WAVELENGTHS)
+    if uniq is None:
+        return None
+    return uniq if uniq.size else None
 
 
 def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64", device: int = 0,
@@ -210,7 +238,7 @@ def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64
     if rays.ndim != 2 or rays.shape[1] != 8:
         raise ValueError(f"rays must have shape (N, 8), got {rays.shape}")
     n = rays.shape[0]
-    uniq = choose_wavelength_table(materials, rays[:, 7])
+    uniq = choose_wavelength_table(materials, rays)
     packed = pack_system(surfaces, materials, uniq)
     mode, idx, n_out = resolve_keep(keep, packed.n_slabs)
     opts = make_opts(mode, idx, precision, reduce)

@@ -175,6 +175,38 @@ def test_continuous_spectrum_uses_in_kernel_sellmeier(rt, rtm, oracle):
         system.ray_trace(rays, rtm.Vacuum(), cauchy)
 
 
+def test_sampled_table_with_unlisted_wavelengths(rt, rtm, oracle):
+    """host batches of Sellmeier media tabulate a 64-ray sample; rays the sample missed are evaluated in the kernel"""
+    from ray_trace_pb_b200 import engine
+    system = systems.relay10_system(rt, rtm)
+    rays = systems.lattice_rays(200, 12.0, 0.0, 0.785)
+    rays[12345, 7] = 0.6328
+    rays[12346:12400, 7] = 1.064
+    rays[777, 7] = np.nan
+    mats = [rtm.Vacuum()] + system.materials + [rtm.Vacuum()]
+    assert engine.choose_wavelength_table(mats, rays).tolist() == [0.785]
+    got = system.ray_trace(rays, rtm.Vacuum(), rtm.Vacuum())
+    want = oracle.ray_trace(system, rays, rtm.Vacuum(), rtm.Vacuum(), n_threads=8)
+    parity.assert_bit_identical(got, want, "unlisted wavelengths")
+
+
+def test_table_only_medium_gets_a_complete_scan(rt, rtm, oracle):
+    """a medium that only exists as Python code needs every distinct wavelength of the batch in the host table"""
+    from ray_trace_pb_b200 import engine
+    system, m_in, m_out, _ = systems.cauchy_singlet(rt, rtm)
+    rays = systems.lattice_rays(150, 15.0, -5.0, 0.5)
+    rays[4321, 7] = 0.45
+    rays[9999:10050, 7] = 0.65
+    mats = [m_in] + system.materials + [m_out]
+    assert engine.choose_wavelength_table(mats, rays).tolist() == [0.45, 0.5, 0.65]
+    got = system.ray_trace(rays, m_in, m_out)
+    want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+    parity.assert_bit_identical(got, want, "complete scan")
+    rays[:, 7] = np.linspace(0.4, 0.7, rays.shape[0])
+    with pytest.raises(NotImplementedError):
+        system.ray_trace(rays, m_in, m_out)
+
+
 def test_distinct_wavelengths_on_device(torch, dev):
     rays = torch.zeros((100_000, 8), dtype=torch.float64, device="cuda")
     wl = np.random.default_rng(0).choice([0.4, 0.5, 0.6, 0.7, np.nan], size=100_000)

@@ -131,6 +131,28 @@ def test_distinct_wavelengths():
     assert engine.distinct_wavelengths(np.array([np.nan]), 16).size == 0
 
 
+def test_host_wavelength_scan_and_table_choice(rt, rtm):
+    """threaded C scan (complete list, for media that only exist as Python code) and the 64-ray sample otherwise"""
+    from ray_trace_pb_b200 import engine
+    rays = np.zeros((300_000, 8))
+    rays[:, 7] = 0.5
+    rays[123_456, 7] = 0.61
+    rays[200_000:200_100, 7] = 0.42
+    rays[17, 7] = np.nan
+    assert engine.distinct_wavelengths_scan(rays).tolist() == [0.42, 0.5, 0.61]
+    rays2 = rays.copy()
+    rays2[:, 7] = np.arange(rays.shape[0])
+    assert engine.distinct_wavelengths_scan(rays2) is None
+    assert engine.distinct_wavelengths_scan(np.full((5, 8), np.nan)).size == 0
+    sellmeier = [rtm.Vacuum(), rtm.Bk7()]
+    assert engine.choose_wavelength_table(sellmeier, rays).tolist() == [0.5]          # sample: kernel covers the rest
+    assert engine.choose_wavelength_table(sellmeier, rays2) is None                   # continuous spectrum
+    custom = [rtm.Vacuum(), rtm.Ebaf11()]
+    assert engine.choose_wavelength_table(custom, rays).tolist() == [0.42, 0.5, 0.61]  # complete
+    assert engine.choose_wavelength_table(custom, rays2) is None
+    assert engine.choose_wavelength_table(custom, np.full((5, 8), np.nan)).tolist() == [1.0]
+
+
 def test_resolve_keep():
     from ray_trace_pb_b200 import _ffi, engine
     assert engine.resolve_keep("all", 7)[::2] == (_ffi.KEEP_ALL, 7)
