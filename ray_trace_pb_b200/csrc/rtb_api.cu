@@ -293,6 +293,14 @@ int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TracePar
         d.grid = r.grid_n > 0 ? r.grid_dev : nullptr;
         if (!d.stats && !d.grid) d.slab = -1;
     }
+    for (int k = 0; k < S; k++) {
+        int act = 0;
+        if (P.slab_pos[2 * k + 1] >= 0) act |= 1;
+        if (P.slab_pos[2 * k + 2] >= 0) act |= 2;
+        if (P.red.slab == 2 * k + 1) act |= 4;
+        if (P.red.slab == 2 * k + 2) act |= 8;
+        P.slab_act[k] = (uint8_t)act;
+    }
     P.src.kind = -1;
     return RTB_OK;
 }

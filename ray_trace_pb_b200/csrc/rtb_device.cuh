@@ -25,7 +25,7 @@ constexpr int kMaxSlabs = 2 * RTB_MAX_SURFACES + 1;
 // launch shape of the trace kernels: 128-thread blocks, register budget for kTraceMinBlocks resident blocks per SM
 constexpr int kTraceThreads = 128;
 #ifndef RTB_TRACE_MIN_BLOCKS
-#define RTB_TRACE_MIN_BLOCKS 6
+#define RTB_TRACE_MIN_BLOCKS 7
 #endif
 constexpr int kTraceMinBlocks = RTB_TRACE_MIN_BLOCKS;
 
@@ -98,6 +98,7 @@ struct TraceParams {
     int32_t flags;              // RTB_FLAG_*
     int32_t pad0;
     int16_t slab_pos[kMaxSlabs + 3]; // output slab position of trace slab j, -1 = not stored
+    uint8_t slab_act[kMaxSurfaces];  // per surface: bit 0 store at-slab, 1 store after-slab, 2 reduce at, 3 reduce after
     DevReduce red;
     DevSource src;
     DevSurface surf[kMaxSurfaces];

@@ -292,14 +292,19 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             const DevSurface &s = P.surf[k];
             const double n2 = !USE_TABLE ? eval_index(P.mat[k + 1], wl0)
                                          : (unlisted ? index_for_unlisted(&P.mat[k + 1], wl0) : s_ntab[row + k + 1]);
-            Ray at, after;
-            const int pa = GENERAL ? P.slab_pos[2 * k + 1] : -1, pb = GENERAL ? P.slab_pos[2 * k + 2] : -1;
-            const bool reduce_at = reducing && P.red.slab == 2 * k + 1;
-            const bool need_at = GENERAL && (pa >= 0 || reduce_at);
+            // what this surface's two slabs are needed for (uniform): bit 0 store "at", 1 store "after",
+            // 2 reduce "at", 3 reduce "after"
+            const int act = GENERAL ? P.slab_act[k] : 0;
+            const bool need_at = (act & 5) != 0;
+            Ray after;
+            auto emit_at = [&](const Ray &at) {
+                if (act & 1) store_ray(P.out + P.slab_pos[2 * k + 1] * P.out_stride, i, at);
+                if (act & 4) reduce_sample(P.red, at, tally);
+            };
             if (dead) {
                 // an all-NaN ray stays all-NaN through every kind of surface: skip the arithmetic
-                set_nan(at);
                 set_nan(after);
+                if (need_at) emit_at(after);
             } else {
                 xm::Rcp rcp_k;
                 rcp_k.b = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
@@ -308,33 +313,35 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                 // run the surface optimistically; one flag says whether every intermediate stayed in the fast
                 // paths' domain, otherwise redo this surface with the Careful arithmetic (surface_steps.cuh)
                 Optimistic m;
+                AtRaw raw;
+                StepResult redo;
                 if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {
                     const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + k] : xm::div(n1, n2);
-                    dead = refracting_step<Optimistic>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only, need_at,
-                                                       at, after);
-                    if (!m.ok) {
-                        const StepResult r = careful_refracting(&s, cur, n1, ratio, !intersect_only);
-                        at = r.at; after = r.after; dead = r.dead;
-                    }
+                    dead = refracting_step<Optimistic>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only, raw, after);
+                    if (!m.ok) redo = careful_refracting(&s, cur, n1, ratio, !intersect_only);
                 } else if (s.kind == RTB_SURF_MIRROR) {
-                    dead = mirror_step<Optimistic>(m, s, cur, n1, rcp_wl, need_at, at, after);
-                    if (!m.ok) {
-                        const StepResult r = careful_mirror(&s, cur, n1);
-                        at = r.at; after = r.after; dead = r.dead;
+                    dead = mirror_step<Optimistic>(m, s, cur, n1, rcp_wl, raw, after);
+                    if (!m.ok) redo = careful_mirror(&s, cur, n1);
+                } else {
+                    dead = perfect_lens_step<Optimistic>(m, s, cur, n1, n2, rcp_wl, rcp_k, intersect_only, need_at, raw,
+                                                         after);
+                    if (!m.ok) redo = careful_lens(&s, cur, n1, n2, intersect_only);
+                }
+                if (m.ok) {
+                    if (need_at) {
+                        Ray at;
+                        fill_at(raw, cur, at);
+                        emit_at(at);
                     }
                 } else {
-                    dead = perfect_lens_step<Optimistic>(m, s, cur, n1, n2, rcp_wl, rcp_k, intersect_only, at, after);
-                    if (!m.ok) {
-                        const StepResult r = careful_lens(&s, cur, n1, n2, intersect_only);
-                        at = r.at; after = r.after; dead = r.dead;
-                    }
+                    if (need_at) emit_at(redo.at);
+                    after = redo.after;
+                    dead = redo.dead;
                 }
             }
             if (GENERAL) {
-                if (pa >= 0) store_ray(P.out + pa * P.out_stride, i, at);
-                if (pb >= 0) store_ray(P.out + pb * P.out_stride, i, after);
-                if (reduce_at) reduce_sample(P.red, at, tally);
-                if (reducing && P.red.slab == 2 * k + 2) reduce_sample(P.red, after, tally);
+                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, i, after);
+                if (act & 8) reduce_sample(P.red, after, tally);
             }
             cur = after;
             n1 = n2;
