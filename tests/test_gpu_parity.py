@@ -44,6 +44,16 @@ def test_golden_history(name, rt, rtm):
         parity.assert_bit_identical(got, g["history"], name)
 
 
+@pytest.mark.parametrize("name", ["relay10", "opm", "edge_mix", "doublet_nlak22", "mirrors"])
+def test_reference_side_stub(name, rt, rtm):
+    """the bare ctypes stub against the C ABI reproduces the reference's history"""
+    import reference_stub
+    g = load_golden(name)
+    system, m_in, m_out = systems.rebuild_system(g["system"], rt, rtm)
+    got = reference_stub.ray_trace(system, g["rays_in"], m_in, m_out)
+    parity.assert_bit_identical(got, g["history"], name)
+
+
 def test_input_shapes(rt, rtm):
     g = load_golden("input_shapes")
     system, m_in, m_out = systems.rebuild_system(g["system"], rt, rtm)
