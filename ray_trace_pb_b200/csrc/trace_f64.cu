@@ -22,6 +22,7 @@
 #include "exact_math.cuh"
 #include "rtb_device.cuh"
 #include "surface_steps.cuh"
+#include "trace_common.cuh"
 
 namespace rtb {
 
@@ -32,195 +33,6 @@ struct SharedConsts {
     double rcp_radius[kMaxSurfaces]; // refined 1/R per spherical surface (1/f for perfect lenses)
     unsigned long long rcp_ok;       // bit k: den_ok of that denominator
 };
-
-// Material.n (materials.py:39-51); Constant.n (materials.py:72-79) ignores the wavelength, NaN included
-__device__ __forceinline__ double eval_index(const DevMaterial &m, double wl)
-{
-    if (m.kind == RTB_MAT_CONSTANT) return m.n_const;
-    if (m.kind == RTB_MAT_TABLE_ONLY) return nan64(); // only the host knows this medium
-    const double w2 = wl * wl;
-    const double acc = (xm::div(m.b0 * w2, w2 - m.c0) + xm::div(m.b1 * w2, w2 - m.c1)) + xm::div(m.b2 * w2, w2 - m.c2);
-    return xm::sqrt(acc + 1.0);
-}
-
-// a ray whose wavelength is not in the host table (the table may be built from a sample of the batch)
-static __device__ __noinline__ double index_for_unlisted(const DevMaterial *m, double wl) { return eval_index(*m, wl); }
-
-// ---- ray I/O ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_ray(const double *base, long long i, Ray &r)
-{
-    const double *p = base + 8 * i;
-    ld256_stream(p, r.ox, r.oy, r.oz, r.dx);
-    ld256_stream(p + 4, r.dy, r.dz, r.ph, r.wl);
-}
-
-__device__ __forceinline__ void store_ray(double *base, long long i, const Ray &r)
-{
-    double *p = base + 8 * i;
-    st256(p, r.ox, r.oy, r.oz, r.dx);
-    st256(p + 4, r.dy, r.dz, r.ph, r.wl);
-}
-
-// on-device ray sources (raytrace.py:45-161 and this library's Cartesian grid); see rtb_source in rtb.h
-__device__ __forceinline__ double linspace_at(long long i, long long n, double start, double step, double stop)
-{
-    const double v = (double)i * step + start;
-    return (n > 1 && i == n - 1) ? stop : v;
-}
-
-__device__ __noinline__ Ray make_ray(const DevSource &g, long long idx)
-{
-    Ray r;
-    r.ph = 0.0;
-    r.wl = g.wavelength;
-    if (g.kind == RTB_SRC_GRID) {
-        const long long iu = idx % g.n_a, iv = idx / g.n_a;
-        const double u = linspace_at(iu, g.n_a, g.a_start, g.a_step, g.a_stop);
-        const double v = linspace_at(iv, g.n_b, g.b_start, g.b_step, g.b_stop);
-        r.ox = (g.px + g.e1x * u) + g.e2x * v;
-        r.oy = (g.py + g.e1y * u) + g.e2y * v;
-        r.oz = (g.pz + g.e1z * u) + g.e2z * v;
-        r.dx = g.axx; r.dy = g.axy; r.dz = g.axz;
-    } else if (g.kind == RTB_SRC_COLLIMATED) {
-        const long long ip = idx % g.n_b, id = idx / g.n_b;
-        const double off = linspace_at(id, g.n_a, g.a_start, g.a_step, g.a_stop);
-        const double phi = ((double)ip * kTwoPi) / (double)g.n_b + g.b_start;
-        double sp, cp;
-        sincos(phi, &sp, &cp);
-        const double a = off * cp, b = off * sp;
-        r.ox = (g.px + g.e1x * a) + g.e2x * b;
-        r.oy = (g.py + g.e1y * a) + g.e2y * b;
-        r.oz = (g.pz + g.e1z * a) + g.e2z * b;
-        r.dx = g.axx; r.dy = g.axy; r.dz = g.axz;
-    } else {
-        const long long it = idx % g.n_a, ip = idx / g.n_a;
-        const double theta = linspace_at(it, g.n_a, g.a_start, g.a_step, g.a_stop);
-        const double phi = ((double)ip * kTwoPi) / (double)g.n_b;
-        double st, ct, sp, cp;
-        sincos(theta, &st, &ct);
-        sincos(phi, &sp, &cp);
-        r.ox = g.px; r.oy = g.py; r.oz = g.pz;
-        r.dx = (g.axx * ct + (g.e1x * cp) * st) + (g.e2x * sp) * st;
-        r.dy = (g.axy * ct + (g.e1y * cp) * st) + (g.e2y * sp) * st;
-        r.dz = (g.axz * ct + (g.e1z * cp) * st) + (g.e2z * sp) * st;
-    }
-    return r;
-}
-
-// ---- fused reductions (rtb_reduce in rtb.h) -----------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_min(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-__device__ __forceinline__ void atomic_min_f64(double *addr, double v)
-{
-    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
-    unsigned long long old = *a;
-    while (v < __longlong_as_double((long long)old)) {
-        const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
-        if (prev == old) break;
-        old = prev;
-    }
-}
-__device__ __forceinline__ void atomic_max_f64(double *addr, double v)
-{
-    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
-    unsigned long long old = *a;
-    while (v > __longlong_as_double((long long)old)) {
-        const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
-        if (prev == old) break;
-        old = prev;
-    }
-}
-
-// Running sums of one thread, flushed once per thread block at the end of the kernel.
-struct Tally {
-    double cnt, su, sv, suu, svv, suv, sp, spp, umin, umax, vmin, vmax;
-};
-
-__device__ __forceinline__ void tally_init(Tally &t)
-{
-    t.cnt = t.su = t.sv = t.suu = t.svv = t.suv = t.sp = t.spp = 0.0;
-    t.umin = t.vmin = CUDART_INF;
-    t.umax = t.vmax = -CUDART_INF;
-}
-
-__device__ __noinline__ void reduce_sample(const DevReduce &R, const Ray r, Tally &t)
-{
-    const double px = r.ox - R.ox, py = r.oy - R.oy, pz = r.oz - R.oz;
-    const double u = dot3(px, py, pz, R.e1x, R.e1y, R.e1z);
-    const double v = dot3(px, py, pz, R.e2x, R.e2y, R.e2z);
-    const double ph = r.ph - R.phase_ref;
-    if (!(isfinite(u) && isfinite(v) && isfinite(ph))) return;
-    if (R.stats) {
-        t.cnt += 1.0;
-        t.su += u; t.sv += v;
-        t.suu += u * u; t.svv += v * v; t.suv += u * v;
-        t.sp += ph; t.spp += ph * ph;
-        t.umin = fmin(t.umin, u); t.umax = fmax(t.umax, u);
-        t.vmin = fmin(t.vmin, v); t.vmax = fmax(t.vmax, v);
-    }
-    if (R.grid) {
-        const double fu = floor((u + R.half_width) * R.inv_cell);
-        const double fv = floor((v + R.half_width) * R.inv_cell);
-        const double g = (double)R.grid_n;
-        if (fu >= 0.0 && fu < g && fv >= 0.0 && fv < g) {
-            const long long cell = (long long)fv * R.grid_n + (long long)fu;
-            const long long plane = (long long)R.grid_n * R.grid_n;
-            double s, c;
-            sincos(ph, &s, &c);
-            atomicAdd(R.grid + cell, c);
-            atomicAdd(R.grid + plane + cell, s);
-            atomicAdd(R.grid + 2 * plane + cell, 1.0);
-        }
-    }
-}
-
-__device__ __noinline__ void tally_flush(const DevReduce &R, Tally &t)
-{
-    if (!R.stats) return;
-    __shared__ double part[12][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-    double v[12] = {warp_sum(t.cnt), warp_sum(t.su),  warp_sum(t.sv),  warp_sum(t.suu),
-                    warp_sum(t.svv), warp_sum(t.suv), warp_sum(t.sp),  warp_sum(t.spp),
-                    warp_min(t.umin), warp_max(t.umax), warp_min(t.vmin), warp_max(t.vmax)};
-    if (lane == 0)
-        for (int k = 0; k < 12; k++) part[k][warp] = v[k];
-    __syncthreads();
-    if (warp == 0) {
-        for (int k = 0; k < 12; k++) {
-            double x;
-            if (k < 8) {
-                x = (lane < nwarp) ? part[k][lane] : 0.0;
-                x = warp_sum(x);
-                if (lane == 0 && x != 0.0) atomicAdd(R.stats + k, x);
-            } else if (k == 8 || k == 10) {
-                x = (lane < nwarp) ? part[k][lane] : CUDART_INF;
-                x = warp_min(x);
-                if (lane == 0 && x < CUDART_INF) atomic_min_f64(R.stats + k, x);
-            } else {
-                x = (lane < nwarp) ? part[k][lane] : -CUDART_INF;
-                x = warp_max(x);
-                if (lane == 0 && x > -CUDART_INF) atomic_max_f64(R.stats + k, x);
-            }
-        }
-    }
-}
 
 // ---- the kernel --------------------------------------------------------------------------------------------
 // USE_TABLE   refractive indices (and n1/n2) from the host table (any material), else in-register Sellmeier.

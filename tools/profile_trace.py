@@ -17,6 +17,7 @@ ap.add_argument("--rays", type=float, default=2e7)
 ap.add_argument("--launches", type=int, default=4)
 ap.add_argument("--keep", default="last")
 ap.add_argument("--reduce", default="none")
+ap.add_argument("--precision", default="f64")
 args = ap.parse_args()
 
 system, materials = bench.relay_system()
@@ -29,7 +30,7 @@ ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.launches + 1)]
 ev[0].record()
 for i in range(args.launches):
     out = dev.trace_tensor(system.surfaces, materials, rays, keep=args.keep, wavelengths=[bench.WAVELENGTH],
-                           reducer=reducer)
+                           reducer=reducer, precision=args.precision)
     ev[i + 1].record()
 torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.launches)]
