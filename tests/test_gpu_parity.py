@@ -390,8 +390,9 @@ def test_f32_mode_tolerance(name, rt, rtm):
     flips = np.isnan(got) != np.isnan(want)
     ray_flips = flips.any(axis=(0, 2)).mean()
     assert ray_flips <= (0.12 if name == "edge_mix" else 0.01), f"{name}: {ray_flips:.3%} of rays changed validity"
-    ok = ~np.isnan(got) & ~np.isnan(want)
-    err = np.abs(got - want)
+    ok = np.isfinite(got) & np.isfinite(want)          # rays parallel to a plane legitimately carry +-inf
+    with np.errstate(invalid="ignore"):
+        err = np.abs(got - want)
     scale = np.abs(want)
     pos_ok = ok[..., 0:3]
     assert err[..., 0:3][pos_ok].max() <= 2e-6 * 1000.0
