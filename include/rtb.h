@@ -242,6 +242,19 @@ int rtb_generate_device(const rtb_source *src, int64_t first_ray, int64_t n_rays
 /* zero / initialise the stats vector and grid referenced by `red` (count=0, min=+inf, max=-inf) */
 int rtb_reduce_init(const rtb_reduce *red, int device, void *stream);
 
+/*
+ * Pupil grid -> PSF (the tail of scripts/2022_02_06_perfect_imaging_system_psf.py:90-105 as a dense complex contraction).
+ * grid_dev is the (3, G, G) accumulator of rtb_reduce; P[v,u] = grid[0] + i grid[1] (divided by grid[2] where non-empty
+ * if normalize_by_count).  Output: n_samples x n_samples samples of E = A P B^T and/or |E|^2 with
+ *   B[k,u] = exp(-2 pi i f_k x_u),  f_k = (k - (n_samples-1)/2) * df,  x_u = (u + 0.5) * (2 half/G) - half  (same for A).
+ * psf_out_dev (n*n) and/or field_re_dev + field_im_dev (n*n each) may be NULL.  scratch_dev: at least
+ * rtb_psf_scratch_doubles() doubles of device memory.
+ */
+int64_t rtb_psf_scratch_doubles(int grid_n, int n_samples, int normalize_by_count);
+int rtb_psf_from_grid_device(const double *grid_dev, int grid_n, double grid_half_width, int n_samples, double df,
+                             int normalize_by_count, double *scratch_dev, int64_t scratch_doubles, double *psf_out_dev,
+                             double *field_re_dev, double *field_im_dev, int device, void *stream);
+
 /* ---- after the trace: replaces intersect_rays, raytrace.py:164-238 ----------------------------------------- */
 /* ray1_dev, ray2_dev : (N, 8) device; pts_out_dev : (N, 3) device. n1 or n2 may be 1 (broadcast). */
 int rtb_intersect_rays_device(const double *ray1_dev, int64_t n1, const double *ray2_dev, int64_t n2,

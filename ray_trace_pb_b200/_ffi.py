@@ -85,7 +85,7 @@ EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_
            "rtb_trace_host", "rtb_trace_source", "rtb_generate_device", "rtb_reduce_init",
            "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
            "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
-           "rtb_selftest_exact_math"]
+           "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device"]
 
 
 def lib():
@@ -115,6 +115,10 @@ def lib():
     L.rtb_distinct_wavelengths_host.restype = i32
     L.rtb_selftest_exact_math.argtypes = [i32, C.c_uint64, i64, C.POINTER(C.c_uint64)]
     L.rtb_selftest_exact_math.restype = i32
+    L.rtb_psf_scratch_doubles.argtypes = [i32, i32, i32]
+    L.rtb_psf_scratch_doubles.restype = i64
+    L.rtb_psf_from_grid_device.argtypes = [vp, i32, C.c_double, i32, C.c_double, i32, vp, i64, vp, vp, vp, i32, vp]
+    L.rtb_psf_from_grid_device.restype = i32
     L.rtb_measure_dfma_rate.argtypes = [i32, dp, dp]
     L.rtb_measure_copy_bandwidth.argtypes = [i32, i64, dp]
     L.rtb_host_alloc.argtypes = [C.c_size_t]

@@ -24,6 +24,9 @@ cudaError_t launch_ray2plane(const double *rays, long long n, const double *norm
                              double *out, double *ts, cudaStream_t stream);
 cudaError_t run_distinct_wavelengths(const double *rays, long long n, double *table_dev, int capacity,
                                      double *host_out, int *n_found, int sm_count, cudaStream_t stream);
+long long psf_scratch_doubles(int G, int M, int normalize);
+cudaError_t launch_psf(const double *grid, int G, double half_width, int M, double df, int normalize, double *scratch,
+                       double *psf_out, double *field_re, double *field_im, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t run_exact_math_selftest(unsigned long long seed, long long n, unsigned long long *bad_host, int sm_count);
 cudaError_t run_dfma_probe(int sm_count, double *dfma_per_s, double *elapsed_ms);
 cudaError_t run_copy_probe(long long bytes, double *bytes_per_s);
@@ -690,6 +693,35 @@ int rtb_distinct_wavelengths_host(const double *rays_host, int64_t n_rays, doubl
     std::sort(vals, vals + n);
     for (int k = 0; k < n; k++) wavelengths_out[k] = vals[k];
     *n_found = n;
+    return RTB_OK;
+}
+
+int64_t rtb_psf_scratch_doubles(int grid_n, int n_samples, int normalize_by_count)
+{
+    if (grid_n <= 0 || n_samples <= 0) return 0;
+    return rtb::psf_scratch_doubles(grid_n, n_samples, normalize_by_count);
+}
+
+int rtb_psf_from_grid_device(const double *grid_dev, int grid_n, double grid_half_width, int n_samples, double df,
+                             int normalize_by_count, double *scratch_dev, int64_t scratch_doubles, double *psf_out_dev,
+                             double *field_re_dev, double *field_im_dev, int device, void *stream)
+{
+    if (!grid_dev || grid_n <= 0 || n_samples <= 0 || !(grid_half_width > 0) || !(df > 0))
+        return fail(RTB_ERR_INVALID, "psf: need a grid, grid_n > 0, n_samples > 0, grid_half_width > 0, df > 0");
+    if (!psf_out_dev && !(field_re_dev && field_im_dev)) return fail(RTB_ERR_INVALID, "psf: no output requested");
+    if (!scratch_dev || scratch_doubles < rtb::psf_scratch_doubles(grid_n, n_samples, normalize_by_count))
+        return fail(RTB_ERR_INVALID, "psf: scratch buffer too small (see rtb_psf_scratch_doubles)");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    int launches = 0;
+    cudaError_t e = rtb::launch_psf(grid_dev, grid_n, grid_half_width, n_samples, df, normalize_by_count, scratch_dev,
+                                    psf_out_dev, field_re_dev, field_im_dev, ctx->sm_count, (cudaStream_t)stream,
+                                    &launches);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "psf launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
     return RTB_OK;
 }
 

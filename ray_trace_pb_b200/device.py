@@ -263,6 +263,30 @@ class Reducer:
             allreduce_stats(self.stats_t)
         return self
 
+    def psf(self, n_samples: int, df: float, normalize_by_count: bool = False, field: bool = False):
+        """
+        PSF from the accumulated pupil grid as a zoomed DFT (kernel zgemm_nt_kernel): ``n_samples x n_samples`` samples
+        of |E|^2, E = A P B^T, at spatial frequencies (k - (n-1)/2) * df along u (columns) and v (rows).  For a lens
+        of focal length f the image coordinate is ``wavelength * f * frequency``.  Returns a CUDA tensor (n, n), or
+        (psf, field_complex) with ``field=True``.
+        """
+        torch = _torch()
+        if self.grid_t is None:
+            raise ValueError("this Reducer was created without a grid")
+        L = _ffi.lib()
+        need = L.rtb_psf_scratch_doubles(self.grid_n, n_samples, int(normalize_by_count))
+        dev = f"cuda:{self.device}"
+        scratch = torch.empty(need, dtype=torch.float64, device=dev)
+        out = torch.empty((n_samples, n_samples), dtype=torch.float64, device=dev)
+        f_re = torch.empty_like(out) if field else None
+        f_im = torch.empty_like(out) if field else None
+        rc = L.rtb_psf_from_grid_device(self.grid_t.data_ptr(), self.grid_n, float(self.struct.grid_half_width),
+                                        n_samples, float(df), int(normalize_by_count), scratch.data_ptr(), need,
+                                        out.data_ptr(), f_re.data_ptr() if field else None,
+                                        f_im.data_ptr() if field else None, self.device, _stream_ptr(self.device))
+        _ffi.check(rc)
+        return (out, torch.complex(f_re, f_im)) if field else out
+
     def stats(self) -> dict:
         """Host copy of the statistics with the derived centroid / RMS radius / RMS wavefront error."""
         v = self.stats_t.cpu().numpy()

@@ -158,6 +158,61 @@ def test_surface_propagate_operator(rt, rtm, oracle):
     parity.assert_bit_identical(cur, want, "chained propagate")
 
 
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_config2_sampled_oracle_and_invariances(rt, rtm, oracle, torch, dev):
+    """
+    BASELINE config 2 at full size: AC508-100-B doublet, 4096 x 4096 pupil grid (16.8 M rays) per wavelength, three
+    wavelengths.  Too big for the oracle as a whole, so: (1) a random 60k-ray sample of each batch is checked bit for
+    bit against the oracle, (2) permuting the rays permutes the result (no cross-ray coupling, no index-dependent
+    arithmetic), (3) two half-launches equal one launch, (4) the fused reduction counts exactly the finite rays.
+    """
+    g = load_golden("doublet_nlak22")
+    system, m_in, m_out = systems.rebuild_system(g["system"], rt, rtm)
+    mats = [m_in] + system.materials + [m_out]
+    rng = np.random.default_rng(42)
+    for wl in (0.7065, 0.855, 1.015):
+        src = dev.RaySource.grid([0, 0, -10.0], 10.0, 4096, wl)
+        rays = src.generate()
+        n = rays.shape[0]
+        assert n == 4096 * 4096
+        red = dev.Reducer(2 * 4 + 1, origin=system.surfaces[4].center)            # at the focal-plane flat
+        last = dev.trace_tensor(system.surfaces, mats, rays, keep="last", wavelengths=[wl], reducer=red)[0]
+        assert int(red.stats()["count"]) == int(torch.isfinite(last[:, 0]).sum()) > 0.99 * n
+        pick = torch.from_numpy(rng.choice(n, size=60_000, replace=False)).cuda()
+        sample_in = rays[pick].cpu().numpy()
+        want = oracle.trace(system.surfaces, mats, sample_in, keep_all=False, n_threads=8)
+        parity.assert_bit_identical(last[pick].cpu().numpy(), want, f"sampled oracle parity, {wl} um")
+        if wl == 0.855:
+            perm = torch.randperm(n, device="cuda")
+            shuffled = dev.trace_tensor(system.surfaces, mats, rays[perm].contiguous(), keep="last", wavelengths=[wl])[0]
+            assert torch.equal(shuffled.view(torch.int64), last[perm].view(torch.int64)), "permutation invariance"
+            half = n // 2 + 77
+            a = dev.trace_tensor(system.surfaces, mats, rays[:half].contiguous(), keep="last", wavelengths=[wl])[0]
+            b = dev.trace_tensor(system.surfaces, mats, rays[half:].contiguous(), keep="last", wavelengths=[wl])[0]
+            assert torch.equal(torch.cat((a, b)).view(torch.int64), last.view(torch.int64)), "launch splitting"
+            fused = dev.trace_source(system.surfaces, mats, src, keep="last")[0]
+            assert torch.equal(fused.view(torch.int64), last.view(torch.int64)), "fused source == materialised rays"
+
+
+def test_full_size_opm_fan_sampled_oracle(rt, rtm, oracle, torch, dev):
+    """BASELINE config 4 shape (ideal OPM, perfect lenses, ray fan generated on the device) at 16 M rays: sampled
+    bit-exact parity with the oracle run on the device-generated rays, plus pupil-grid mass conservation."""
+    system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
+    mats = [m_in] + system.materials + [m_out]
+    src = dev.RaySource.fan([1e-3, 1e-3, 1e-3 * np.tan(theta)], alpha1, 4001, 532e-6, nphis=4000)
+    slab = 2 * 8 + 2
+    o3n = system.surfaces[8].normal
+    e2 = np.array([0.0, 1.0, 0.0])
+    red = dev.Reducer(slab, origin=system.surfaces[8].center, e1=np.cross(e2, o3n), e2=e2, grid_n=512, half_width=3.2)
+    rays = src.generate()
+    last = dev.trace_tensor(system.surfaces, mats, rays, keep="last", wavelengths=[532e-6], reducer=red)[0]
+    pick = torch.from_numpy(np.random.default_rng(1).choice(rays.shape[0], size=50_000, replace=False)).cuda()
+    want = oracle.trace(system.surfaces, mats, rays[pick].cpu().numpy(), keep_all=False, n_threads=8)
+    parity.assert_bit_identical(last[pick].cpu().numpy(), want, "sampled oracle parity, OPM fan")
+    stats = red.stats()
+    assert float(red.grid[2].sum()) == stats["count"] > 0.5 * rays.shape[0]     # every counted ray landed in the grid
+
+
 # ------------------------------------------------------------------------------------------------ refractive indices
 def test_formula_mode_equals_table_mode(rt, rtm, torch, dev):
     system = systems.relay10_system(rt, rtm)
@@ -320,6 +375,83 @@ def test_reduction_at_input_and_with_source(rt, rtm, oracle, dev):
         assert got[0] == want[0]
         np.testing.assert_allclose(got[1:8], want[1:8], rtol=1e-10, atol=1e-6)
         assert np.array_equal(red.grid.cpu().numpy()[2], oracle.reduce_grid(hist[slab], (0, 0, 0), (1, 0, 0), (0, 1, 0), 32, 21.0)[2])
+
+
+# ------------------------------------------------------------------------------------------------ pupil grid -> PSF
+def _dft_matrix(m, g, df, half):
+    cell = 2 * half / g
+    f = (np.arange(m) - 0.5 * (m - 1)) * df
+    x = (np.arange(g) + 0.5) * cell - half
+    return np.exp(-2j * np.pi * np.outer(f, x))
+
+
+def test_psf_contraction_matches_numpy(dev, torch):
+    """E = A P B^T against NumPy with the same definition, and against fftshift(fft2(ifftshift(P))) for odd sizes"""
+    rng = np.random.default_rng(3)
+    for g, m, df_scale in ((95, 95, 1.0), (128, 33, 0.37), (200, 70, 2.1)):
+        half = 1.7
+        red = dev.Reducer(0, grid_n=g, half_width=half)
+        grid = rng.standard_normal((3, g, g))
+        grid[2] = rng.integers(0, 4, (g, g))
+        red.grid[...] = torch.from_numpy(grid).cuda()
+        df = df_scale / (2 * half)
+        psf, field = red.psf(m, df, field=True)
+        d = _dft_matrix(m, g, df, half)
+        want = d @ (grid[0] + 1j * grid[1]) @ d.T
+        scale = np.abs(want).max()
+        np.testing.assert_allclose(field.cpu().numpy(), want, rtol=0, atol=2e-12 * scale)
+        np.testing.assert_allclose(psf.cpu().numpy(), np.abs(want) ** 2, rtol=0, atol=4e-12 * scale**2)
+        with np.errstate(all="ignore"):
+            pn = np.where(grid[2] > 0, (grid[0] + 1j * grid[1]) / grid[2], 0)
+        got_n = red.psf(m, df, normalize_by_count=True).cpu().numpy()
+        np.testing.assert_allclose(got_n, np.abs(d @ pn @ d.T) ** 2, rtol=0, atol=4e-12 * np.abs(d @ pn @ d.T).max() ** 2)
+        if g == m and g % 2 == 1 and df_scale == 1.0:
+            p = grid[0] + 1j * grid[1]
+            fft = np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(p)))
+            np.testing.assert_allclose(field.cpu().numpy(), fft, rtol=0, atol=2e-12 * scale)
+
+
+def test_psf_airy_known_answer(rt, rtm, dev, torch):
+    """
+    The reference's PSF known answer (scripts/2022_02_06_perfect_imaging_system_psf.py:168-171): an NA-limited
+    perfect imaging system images an on-axis point to the Airy pattern |2 J1(v)/v|^2.  Here: device fan -> fused trace
+    -> pupil grid at the pupil flat -> zoomed-DFT PSF.
+    """
+    from scipy.special import j1
+    wavelength, na, f1, f2 = 0.532e-3, 0.3, 3.0, 30.0
+    alpha = np.arcsin(na)
+    system = rt.System([rt.PerfectLens(f1, [0, 0, f1], [0, 0, 1], alpha),
+                        rt.FlatSurface([0, 0, 2 * f1], [0, 0, 1], 3 * f1),
+                        rt.PerfectLens(f2, [0, 0, 2 * f1 + f2], [0, 0, 1], alpha),
+                        rt.FlatSurface([0, 0, 2 * f1 + 2 * f2], [0, 0, 1], 10.)],
+                       [rtm.Vacuum(), rtm.Vacuum(), rtm.Vacuum()])
+    mats = [rtm.Vacuum()] * 5
+    chief = system.ray_trace(np.array([0, 0, 0, 0, 0, 1.0, 0, wavelength]), rtm.Vacuum(), rtm.Vacuum())
+    phase_ref = float(chief[4, 0, 6])                                   # slab 4 = just after the pupil flat
+    src = dev.RaySource.fan([0, 0, 0], alpha * (1 - 1e-9), 2001, wavelength, nphis=2000)
+    r_pupil = f1 * na
+    red = dev.Reducer(4, origin=(0, 0, 2 * f1), grid_n=256, half_width=1.0, phase_ref=phase_ref)
+    dev.trace_source(system.surfaces, mats, src, keep="none", reducer=red)
+    grid = red.grid.cpu().numpy()
+    filled = grid[2] > 0
+    # constant phase across the pupil: every filled cell's mean phasor is 1
+    phasor = (grid[0] + 1j * grid[1])[filled] / grid[2][filled]
+    assert np.abs(phasor - 1).max() < 1e-5
+    # filled cells = the disk of radius f1 * NA
+    c = (np.arange(256) + 0.5) * (2.0 / 256) - 1.0
+    rr = np.hypot(*np.meshgrid(c, c))
+    assert filled[rr < r_pupil - 0.02].all() and not filled[rr > r_pupil + 0.02].any()
+    m, df = 65, 0.05
+    psf = red.psf(m, df, normalize_by_count=True).cpu().numpy()
+    psf /= psf[m // 2, m // 2]
+    f = (np.arange(m) - (m - 1) / 2) * df
+    v = 2 * np.pi * np.hypot(*np.meshgrid(f, f)) * r_pupil
+    with np.errstate(all="ignore"):
+        airy = np.where(v > 0, (2 * j1(v) / v) ** 2, 1.0)
+    assert np.abs(psf - airy).max() < 0.01
+    row = psf[m // 2, m // 2:]
+    first_min = f[m // 2:][np.argmax(np.diff(row) > 0)]
+    assert abs(first_min - 3.8317 / (2 * np.pi * r_pupil)) <= df
 
 
 # ------------------------------------------------------------------------------------------------ helpers

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/../ray_trace_pb_b200/csrc"
 for mb in "$@"; do
   mkdir -p ../_lib/var$mb
-  for f in rtb_api trace_f64 trace_f32 aux_kernels; do
+  for f in rtb_api trace_f64 trace_f32 aux_kernels psf_kernels; do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v \
       -DRTB_TRACE_MIN_BLOCKS=$mb -c $f.cu -o ../_lib/var$mb/$f.o 2> ../_lib/var$mb/$f.log &
   done
