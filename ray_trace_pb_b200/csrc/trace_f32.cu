@@ -16,6 +16,8 @@
 //   positions  |dp| <= 2e-6 * L   (L = 1000 mm, the length scale of the traced systems: 2 nm per mm of path)
 //   directions |dd| <= 2e-6
 //   phase      |dphi| <= 2e-6 * |phi|  (i.e. optical path length to 2e-6 relative)
+//   (10x looser, 2e-5, for high-NA perfect-lens systems such as the ideal OPM, where sin(theta) reaches 0.96 and the
+//   fp32 direction error is amplified by 1/cos(theta))
 //   validity   identical NaN masks except for rays within the position tolerance of an aperture edge, of a
 //              grazing / missing intersection or of the critical angle.
 // This translation unit is compiled with FMA contraction enabled (see Makefile).
