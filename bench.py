@@ -236,6 +236,11 @@ def main():
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
+    traffic_per_ray = None
+    try:
+        traffic_per_ray = float(json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())["dram_bytes_per_ray"])
+    except Exception:
+        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
 
@@ -323,7 +328,10 @@ def main():
                        "l2": "inputs (8 GB/GPU at the default size) are larger than L2; no flush needed",
                        "valid_rays_rank0": n_valid, "parity": "fp64 bit-exact mode"},
             "roofline": {"bound": "fp64", "achieved": achieved_inst / 1e9, "peak": dfma.value / 1e9,
-                         "unit": "G FP64-pipe instr/s", "frac": achieved_inst / dfma.value, "traffic": None,
+                         "unit": "G FP64-pipe instr/s", "frac": achieved_inst / dfma.value,
+                         "traffic": None if traffic_per_ray is None else traffic_per_ray * n_rays,
+                         "traffic_note": "DRAM bytes per launch = ncu dram__bytes_read+write per ray (profiles/r01_traffic.json) "
+                                         "x rays of this launch; algorithmic = 128 B/ray",
                          "peak_source": "DFMA register micro-benchmark run in this process (rtb_measure_dfma_rate)",
                          "algorithmic_instr_per_ray": I_ALG_PER_RAY, "kernel_ms": kernel_ms_mean,
                          "flops_form": {"achieved_tflops": F_ALG_PER_RAY * rays_per_s_gpu / 1e12,
