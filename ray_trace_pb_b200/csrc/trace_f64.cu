@@ -151,14 +151,19 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                     dead = redo.dead;
                 }
             }
-            if (GENERAL) {
-                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, i, after);
-                if (act & 8) reduce_sample(P.red, after, tally);
+            if (GENERAL && (act & 10)) {
+                Ray out = after;
+                if (dead) set_nan(out); // the optimistic step leaves a culled ray's values un-blanked
+                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, i, out);
+                if (act & 8) reduce_sample(P.red, out, tally);
             }
             cur = after;
             n1 = n2;
         }
-        if (!GENERAL) store_ray(P.out, i, cur);
+        if (!GENERAL) {
+            if (dead) set_nan(cur);
+            store_ray(P.out, i, cur);
+        }
     }
     if (GENERAL && reducing) tally_flush(P.red, tally);
 }
