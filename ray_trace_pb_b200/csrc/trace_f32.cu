@@ -75,7 +75,7 @@ __device__ __forceinline__ RayM narrow(const Ray &r)
 // per-surface constants in fp32
 struct SurfF {
     float nx, ny, nz, ax, ay, az;
-    float inv_radius, focal_len, sin_alpha;
+    float inv_radius, aperture_sq, focal_len, sin_alpha;
 };
 
 __device__ __forceinline__ SurfF surf_f32(const DevSurface &s, float inv_radius)
@@ -84,24 +84,22 @@ __device__ __forceinline__ SurfF surf_f32(const DevSurface &s, float inv_radius)
     f.nx = (float)s.nx; f.ny = (float)s.ny; f.nz = (float)s.nz;
     f.ax = (float)s.ax; f.ay = (float)s.ay; f.az = (float)s.az;
     f.inv_radius = inv_radius; // 1/R, computed once per block
+    f.aperture_sq = (float)(s.aperture * s.aperture);
     f.focal_len = (float)s.focal_len;
     f.sin_alpha = (float)s.sin_alpha;
     return f;
 }
 
 // ray -> plane through (cx, cy, cz) with normal n; t in fp32, position and phase in fp64.  Returns t.
-// (double <-> float conversions run on the quarter-rate XU pipe, so the direction is widened once per surface
-// and passed in as (ddx, ddy, ddz).)
-__device__ __forceinline__ float to_plane_f(const RayM &in, double ddx, double ddy, double ddz, float nx, float ny,
-                                            float nz, double cx, double cy, double cz, double k_n, double &px, double &py,
-                                            double &pz, double &ph)
+__device__ __forceinline__ float to_plane_f(const RayM &in, float nx, float ny, float nz, double cx, double cy, double cz,
+                                            double k_n, double &px, double &py, double &pz, double &ph)
 {
     const float rx = (float)(in.ox - cx), ry = (float)(in.oy - cy), rz = (float)(in.oz - cz);
     const float t = -dot3f(rx, ry, rz, nx, ny, nz) / dot3f(in.dx, in.dy, in.dz, nx, ny, nz);
     const double td = (double)t;
-    px = fma(ddx, td, in.ox);
-    py = fma(ddy, td, in.oy);
-    pz = fma(ddz, td, in.oz);
+    px = fma((double)in.dx, td, in.ox);
+    py = fma((double)in.dy, td, in.oy);
+    pz = fma((double)in.dz, td, in.oz);
     ph = fma(td, k_n, in.ph); // |d t| sign(t) k n with |d| = 1
     return t;
 }
@@ -153,41 +151,39 @@ __device__ __forceinline__ void fill_at_f(bool kill, double px, double py, doubl
 
 // flat / sphere refraction and plane mirror (raytrace.py:1160-1303)
 __device__ __forceinline__ bool bend_step(const DevSurface &s, const RayM &in, double k, double n1, double ratio,
-                                          float inv_radius, bool front_cull, bool need_at, RayM &at, RayM &after)
+                                          float inv_radius, bool front_cull, RayM &at, RayM &after)
 {
     const SurfF f = surf_f32(s, inv_radius);
-    const double ddx = (double)in.dx, ddy = (double)in.dy, ddz = (double)in.dz;
-    const double ap_sq = s.aperture * s.aperture;
     double px, py, pz, ph;
     float nx, ny, nz;
     bool kill = false, on;
     if (s.kind == RTB_SURF_SPHERE) {
         // quadratic in fp64 (raytrace.py:1497-1509), root in fp32
         const double qx = in.ox - s.cx, qy = in.oy - s.cy, qz = in.oz - s.cz;
-        const double b = fma(ddz, qz, fma(ddy, qy, ddx * qx));
+        const double b = fma((double)in.dz, qz, fma((double)in.dy, qy, (double)in.dx * qx));
         const double cq = fma(qz, qz, fma(qy, qy, qx * qx)) - s.radius_sq;
         const double root = (double)sqrtf((float)fma(b, b, -cq));
         const double t1 = root - b, t2 = -b - root;
         double t = (t2 < 0.0) ? t1 : t2;
         t = (t1 < 0.0 || root != root) ? CUDART_NAN : t;
-        px = fma(ddx, t, in.ox);
-        py = fma(ddy, t, in.oy);
-        pz = fma(ddz, t, in.oz);
+        px = fma((double)in.dx, t, in.ox);
+        py = fma((double)in.dy, t, in.oy);
+        pz = fma((double)in.dz, t, in.oz);
         ph = fma(t, k * n1, in.ph);
-        const double rx = px - s.cx, ry = py - s.cy, rz = pz - s.cz;
-        nx = (float)rx * f.inv_radius;
-        ny = (float)ry * f.inv_radius;
-        nz = (float)rz * f.inv_radius;
-        // aperture measured from the axis through the origin (raytrace.py:1530-1533), in fp64 (cheaper than converting)
-        const double along = fma(pz, s.az, fma(py, s.ay, px * s.ax));
-        const double ux = fma(-along, s.ax, px), uy = fma(-along, s.ay, py), uz = fma(-along, s.az, pz);
-        on = fma(uz, uz, fma(uy, uy, ux * ux)) <= ap_sq;
+        nx = (float)(px - s.cx) * f.inv_radius;
+        ny = (float)(py - s.cy) * f.inv_radius;
+        nz = (float)(pz - s.cz) * f.inv_radius;
+        // aperture measured from the axis through the origin (raytrace.py:1530-1533)
+        const float fx = (float)px, fy = (float)py, fz = (float)pz;
+        const float along = dot3f(fx, fy, fz, f.ax, f.ay, f.az);
+        const float ux = fmaf(-along, f.ax, fx), uy = fmaf(-along, f.ay, fy), uz = fmaf(-along, f.az, fz);
+        on = dot3f(ux, uy, uz, ux, uy, uz) <= f.aperture_sq;
     } else {
-        const float t = to_plane_f(in, ddx, ddy, ddz, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n1, px, py, pz, ph);
+        const float t = to_plane_f(in, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n1, px, py, pz, ph);
         kill = t < 0.0f;
         nx = f.nx; ny = f.ny; nz = f.nz;
-        const double rx = px - s.cx, ry = py - s.cy, rz = pz - s.cz;
-        on = fma(rz, rz, fma(ry, ry, rx * rx)) <= ap_sq;
+        const float rx = (float)(px - s.cx), ry = (float)(py - s.cy), rz = (float)(pz - s.cz);
+        on = dot3f(rx, ry, rz, rx, ry, rz) <= f.aperture_sq;
     }
     const bool mirror = s.kind == RTB_SURF_MIRROR;
     if (front_cull && !mirror) kill = kill || (dot3f(in.dx, in.dy, in.dz, f.ax, f.ay, f.az) < 0.0f);
@@ -195,20 +191,19 @@ __device__ __forceinline__ bool bend_step(const DevSurface &s, const RayM &in, d
     float ex, ey, ez;
     bend(in.dx, in.dy, in.dz, nx, ny, nz, (float)ratio, mirror, ex, ey, ez);
     finish(on, px, py, pz, ex, ey, ez, ph, in.wl, after);
-    if (need_at) fill_at_f(kill, px, py, pz, ph, in, at);
+    fill_at_f(kill, px, py, pz, ph, in, at);
     return !on;
 }
 
 // PerfectLens.propagate (raytrace.py:1601-1801)
 __device__ __forceinline__ bool lens_step(const DevSurface &s, const RayM &in, double k, double n1, double n2,
-                                          bool as_get_intersect, bool need_before, RayM &before, RayM &after)
+                                          bool as_get_intersect, RayM &before, RayM &after)
 {
     const SurfF f = surf_f32(s, 0.0f);
     const double fx = fma(-s.nfx, n1, s.cx), fy = fma(-s.nfy, n1, s.cy), fz = fma(-s.nfz, n1, s.cz);
     const double gx = fma(s.nfx, n2, s.cx), gy = fma(s.nfy, n2, s.cy), gz = fma(s.nfz, n2, s.cz);
     double ax, ay, az, ph_ffp;
-    const double ddx = (double)in.dx, ddy = (double)in.dy, ddz = (double)in.dz;
-    to_plane_f(in, ddx, ddy, ddz, f.nx, f.ny, f.nz, fx, fy, fz, k * n1, ax, ay, az, ph_ffp);
+    to_plane_f(in, f.nx, f.ny, f.nz, fx, fy, fz, k * n1, ax, ay, az, ph_ffp);
 
     const float rnd = dot3f(in.dx, in.dy, in.dz, f.nx, f.ny, f.nz);
     float px = fmaf(-rnd, f.nx, in.dx), py = fmaf(-rnd, f.ny, in.dy), pz = fmaf(-rnd, f.nz, in.dz);
@@ -242,16 +237,13 @@ __device__ __forceinline__ bool lens_step(const DevSurface &s, const RayM &in, d
     const double plane_wave = (double)dot3f(hx, hy, hz, in.dx, in.dy, in.dz);
     rb.ph = (ph_ffp - (k * n1) * plane_wave) + k * ((n1 * n1) * s.focal_len + (n2 * n2) * s.focal_len);
 
-    to_plane_f(rb, (double)rb.dx, (double)rb.dy, (double)rb.dz, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n2, after.ox,
-               after.oy, after.oz, after.ph);
+    to_plane_f(rb, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n2, after.ox, after.oy, after.oz, after.ph);
     after.dx = rb.dx; after.dy = rb.dy; after.dz = rb.dz;
     after.wl = rb.wl;
-    if (need_before) {
-        before = in;
-        const float tb = to_plane_f(in, ddx, ddy, ddz, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n1, before.ox, before.oy,
-                                    before.oz, before.ph);
-        if (as_get_intersect && tb < 0.0f) set_nan(before);
-    }
+    before = in;
+    const float tb = to_plane_f(in, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n1, before.ox, before.oy, before.oz,
+                                before.ph);
+    if (as_get_intersect && tb < 0.0f) set_nan(before);
     return culled;
 }
 
@@ -313,10 +305,10 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                 set_nan(at);
                 set_nan(after);
             } else if (s.kind == RTB_SURF_PERFECT_LENS) {
-                dead = lens_step(s, cur, k, n1, n2, intersect_only, (act & 5) != 0, at, after);
+                dead = lens_step(s, cur, k, n1, n2, intersect_only, at, after);
             } else {
                 const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + q] : n1 / n2;
-                dead = bend_step(s, cur, k, n1, ratio, s_inv_radius[q], !intersect_only, (act & 5) != 0, at, after);
+                dead = bend_step(s, cur, k, n1, ratio, s_inv_radius[q], !intersect_only, at, after);
             }
             if (act & 5) {
                 const Ray w = widen(at);
