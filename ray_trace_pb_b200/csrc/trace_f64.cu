@@ -129,10 +129,15 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                 StepResult redo;
                 if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {
                     const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + k] : xm::div(n1, n2);
-                    dead = refracting_step<Optimistic>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only, raw, after);
+                    // two instantiations so that the at-surface values are only kept alive where they are consumed
+                    dead = need_at ? refracting_step<Optimistic, true>(m, s, cur, n1, ratio, rcp_wl, rcp_k,
+                                                                       !intersect_only, raw, after)
+                                   : refracting_step<Optimistic, false>(m, s, cur, n1, ratio, rcp_wl, rcp_k,
+                                                                        !intersect_only, raw, after);
                     if (!m.ok) redo = careful_refracting(&s, cur, n1, ratio, !intersect_only);
                 } else if (s.kind == RTB_SURF_MIRROR) {
-                    dead = mirror_step<Optimistic>(m, s, cur, n1, rcp_wl, raw, after);
+                    dead = need_at ? mirror_step<Optimistic, true>(m, s, cur, n1, rcp_wl, raw, after)
+                                   : mirror_step<Optimistic, false>(m, s, cur, n1, rcp_wl, raw, after);
                     if (!m.ok) redo = careful_mirror(&s, cur, n1);
                 } else {
                     dead = perfect_lens_step<Optimistic>(m, s, cur, n1, n2, rcp_wl, rcp_k, intersect_only, need_at, raw,

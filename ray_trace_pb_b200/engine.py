@@ -239,6 +239,8 @@ def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64
         raise ValueError(f"rays must have shape (N, 8), got {rays.shape}")
     n = rays.shape[0]
     uniq = choose_wavelength_table(materials, rays)
+    if uniq is None and any(pack_material(m).kind == KIND_TABLE_ONLY for m in materials):
+        return _trace_host_grouped(surfaces, materials, rays, keep, precision, device, reduce, out)
     packed = pack_system(surfaces, materials, uniq)
     mode, idx, n_out = resolve_keep(keep, packed.n_slabs)
     opts = make_opts(mode, idx, precision, reduce)
@@ -249,4 +251,42 @@ def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64
     rc = _ffi.lib().rtb_trace_host(C.byref(packed.sys), rays.ctypes.data, n, out.ctypes.data if n_out else None,
                                    C.byref(opts), device)
     _ffi.check(rc)
+    return out
+
+
+MAX_WAVELENGTH_GROUPS = 16
+
+
+def _trace_host_grouped(surfaces, materials, rays, keep, precision, device, reduce, out):
+    """
+    A batch with more than RTB_MAX_WAVELENGTHS distinct wavelengths AND media that only exist as Python code: the
+    rays are traced in groups of RTB_MAX_WAVELENGTHS wavelengths, each group with its own complete host table
+    (the GPU still does all the ray arithmetic; the host only selects and scatters rows).
+    """
+    wl = rays[:, 7]
+    valid = ~np.isnan(wl)
+    all_wl = np.unique(wl[valid])
+    width = _ffi.RTB_MAX_WAVELENGTHS
+    if all_wl.size > width * MAX_WAVELENGTH_GROUPS:
+        bad = sorted({type(m).__name__ for m in materials if pack_material(m).kind == KIND_TABLE_ONLY})
+        raise NotImplementedError(
+            f"media {bad} define their own n() and the batch has {all_wl.size} distinct wavelengths; at most "
+            f"{width * MAX_WAVELENGTH_GROUPS} are supported for host-evaluated media (no CPU fallback)")
+    n = rays.shape[0]
+    mode, idx, n_out = resolve_keep(keep, 2 * len(surfaces) + 1)
+    if out is None:
+        out = np.empty((n_out, n, 8), dtype=np.float64)
+    elif out.shape != (n_out, n, 8):
+        raise ValueError(f"out must have shape {(n_out, n, 8)}")
+    for g in range(0, max(all_wl.size, 1), width):
+        group = all_wl[g:g + width]
+        sel = np.isin(wl, group)
+        if g == 0:
+            sel |= ~valid                        # NaN-wavelength rays ride with the first group (table's NaN row)
+        if not sel.any():
+            continue
+        part = trace_host(surfaces, materials, np.ascontiguousarray(rays[sel]), keep=keep, precision=precision,
+                          device=device, reduce=reduce)
+        if n_out:
+            out[:, sel, :] = part
     return out

@@ -267,6 +267,13 @@ def test_table_only_medium_gets_a_complete_scan(rt, rtm, oracle):
     got = system.ray_trace(rays, m_in, m_out)
     want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
     parity.assert_bit_identical(got, want, "complete scan")
+    # more distinct wavelengths than one table holds: traced in wavelength groups, still exact
+    rays[:, 7] = np.random.default_rng(0).choice(np.linspace(0.4, 0.7, 37), size=rays.shape[0])
+    rays[11, 7] = np.nan
+    got = system.ray_trace(rays, m_in, m_out)
+    want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+    parity.assert_bit_identical(got, want, "37 wavelengths in groups of 8")
+    parity.assert_bit_identical(system.ray_trace(rays, m_in, m_out, keep="last")[0], want[-1], "grouped, keep=last")
     rays[:, 7] = np.linspace(0.4, 0.7, rays.shape[0])
     with pytest.raises(NotImplementedError):
         system.ray_trace(rays, m_in, m_out)
