@@ -161,6 +161,9 @@ typedef struct rtb_reduce {
                                      1398-1403, 1479-1516, 1580-1584): no front-side cull; a perfect lens blanks
                                      rays that would have to travel backwards.  Used by the per-surface operator. */
 
+#define RTB_FLAG_PLANES_IN 2      /* device entry points only: rays_in_dev is (8, N) -- one plane per column           */
+#define RTB_FLAG_PLANES_OUT 4     /* device entry points only: out_dev is (n_slabs, 8, N)                              */
+
 typedef struct rtb_trace_opts {
     int32_t precision; /* rtb_precision */
     int32_t keep_mode; /* rtb_keep_mode */

@@ -35,6 +35,8 @@ F64_EXACT, F32_FAST = 0, 1
 KEEP_ALL, KEEP_LAST, KEEP_LIST, KEEP_NONE = 0, 1, 2, 3
 SRC_COLLIMATED, SRC_FAN, SRC_GRID = 0, 1, 2
 FLAG_INTERSECT_ONLY = 1
+FLAG_PLANES_IN = 2
+FLAG_PLANES_OUT = 4
 
 _d3 = C.c_double * 3
 

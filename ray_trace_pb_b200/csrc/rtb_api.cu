@@ -453,6 +453,8 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
     if (n_rays < 0) return fail(RTB_ERR_INVALID, "n_rays = %lld is negative", (long long)n_rays);
     if (n_rays == 0) return RTB_OK;
     if (!rays_in_host) return fail(RTB_ERR_INVALID, "rays_in_host is NULL");
+    if (opts->flags & (RTB_FLAG_PLANES_IN | RTB_FLAG_PLANES_OUT))
+        return fail(RTB_ERR_UNSUPPORTED, "the plane (8, N) layouts are offered by the device entry points only");
     const int slabs = n_out_slabs(sys, opts);
     if (slabs > 0 && !out_host) return fail(RTB_ERR_INVALID, "out_host is NULL but the keep mode stores rays");
     DeviceCtx *ctx;

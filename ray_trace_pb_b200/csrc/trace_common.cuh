@@ -26,15 +26,30 @@ __device__ __forceinline__ double eval_index(const DevMaterial &m, double wl)
 static __device__ __noinline__ double index_for_unlisted(const DevMaterial *m, double wl) { return eval_index(*m, wl); }
 
 // ---- ray I/O ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_ray(const double *base, long long i, Ray &r)
+// Two layouts (rtb_trace_opts.flags): rows of 8 doubles -- the reference's (N, 8), moved as two 256-bit accesses per
+// ray so every 32-byte sector is used whole -- or planes (8, N), where each of the eight accesses of a warp is one
+// contiguous 256-byte run.
+__device__ __forceinline__ void load_ray(const double *base, long long i, long long n, bool planes, Ray &r)
 {
+    if (planes) {
+        r.ox = __ldg(base + i);         r.oy = __ldg(base + n + i);     r.oz = __ldg(base + 2 * n + i);
+        r.dx = __ldg(base + 3 * n + i); r.dy = __ldg(base + 4 * n + i); r.dz = __ldg(base + 5 * n + i);
+        r.ph = __ldg(base + 6 * n + i); r.wl = __ldg(base + 7 * n + i);
+        return;
+    }
     const double *p = base + 8 * i;
     ld256_stream(p, r.ox, r.oy, r.oz, r.dx);
     ld256_stream(p + 4, r.dy, r.dz, r.ph, r.wl);
 }
 
-__device__ __forceinline__ void store_ray(double *base, long long i, const Ray &r)
+__device__ __forceinline__ void store_ray(double *base, long long i, long long n, bool planes, const Ray &r)
 {
+    if (planes) {
+        base[i] = r.ox;         base[n + i] = r.oy;     base[2 * n + i] = r.oz;
+        base[3 * n + i] = r.dx; base[4 * n + i] = r.dy; base[5 * n + i] = r.dz;
+        base[6 * n + i] = r.ph; base[7 * n + i] = r.wl;
+        return;
+    }
     double *p = base + 8 * i;
     st256(p, r.ox, r.oy, r.oz, r.dx);
     st256(p + 4, r.dy, r.dz, r.ph, r.wl);

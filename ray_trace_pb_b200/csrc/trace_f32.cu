@@ -268,13 +268,15 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
     Tally tally;
     tally_init(tally);
 
+    const bool planes_in = (P.flags & RTB_FLAG_PLANES_IN) != 0, planes_out = (P.flags & RTB_FLAG_PLANES_OUT) != 0;
+    const long long out_rows = P.out_stride / 8;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_rays; i += stride) {
         Ray first;
         if (FROM_SOURCE)
             first = make_ray(P.src, P.src.first + i);
         else
-            load_ray(P.rays_in, i, first);
+            load_ray(P.rays_in, i, P.n_rays, planes_in, first);
         RayM cur = narrow(first);
         const double wl0 = cur.wl;
         const double k = kTwoPi / wl0;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
             unlisted = (row == P.n_wl) && (wl0 == wl0);
             row *= n_med;
         }
-        if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, i, first);
+        if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, i, out_rows, planes_out, first);
         if (reducing && P.red.slab == 0) reduce_sample(P.red, first, tally);
 
         double n1 = !USE_TABLE ? eval_index(P.mat[0], wl0) : (unlisted ? index_for_unlisted(&P.mat[0], wl0) : s_ntab[row]);
@@ -312,12 +314,12 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
             }
             if (act & 5) {
                 const Ray w = widen(at);
-                if (act & 1) store_ray(P.out + P.slab_pos[2 * q + 1] * P.out_stride, i, w);
+                if (act & 1) store_ray(P.out + P.slab_pos[2 * q + 1] * P.out_stride, i, out_rows, planes_out, w);
                 if (act & 4) reduce_sample(P.red, w, tally);
             }
             if (act & 10) {
                 const Ray w = widen(after);
-                if (act & 2) store_ray(P.out + P.slab_pos[2 * q + 2] * P.out_stride, i, w);
+                if (act & 2) store_ray(P.out + P.slab_pos[2 * q + 2] * P.out_stride, i, out_rows, planes_out, w);
                 if (act & 8) reduce_sample(P.red, w, tally);
             }
             cur = after;

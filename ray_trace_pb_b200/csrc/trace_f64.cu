@@ -68,13 +68,15 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
     Tally tally;
     if (GENERAL) tally_init(tally);
 
+    const bool planes_in = (P.flags & RTB_FLAG_PLANES_IN) != 0, planes_out = (P.flags & RTB_FLAG_PLANES_OUT) != 0;
+    const long long out_rows = P.out_stride / 8;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_rays; i += stride) {
         Ray cur;
         if (FROM_SOURCE)
             cur = make_ray(P.src, P.src.first + i);
         else
-            load_ray(P.rays_in, i, cur);
+            load_ray(P.rays_in, i, P.n_rays, planes_in, cur);
 
         // refractive indices are functions of the launch wavelength; see DESIGN.md ("n is taken at launch")
         const double wl0 = cur.wl;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             row *= n_med;
         }
         if (GENERAL) {
-            if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, i, cur);
+            if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, i, out_rows, planes_out, cur);
             if (reducing && P.red.slab == 0) reduce_sample(P.red, cur, tally);
         }
 
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             const bool need_at = (act & 5) != 0;
             Ray after;
             auto emit_at = [&](const Ray &at) {
-                if (act & 1) store_ray(P.out + P.slab_pos[2 * k + 1] * P.out_stride, i, at);
+                if (act & 1) store_ray(P.out + P.slab_pos[2 * k + 1] * P.out_stride, i, out_rows, planes_out, at);
                 if (act & 4) reduce_sample(P.red, at, tally);
             };
             if (dead) {
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             if (GENERAL && (act & 10)) {
                 Ray out = after;
                 if (dead) set_nan(out); // the optimistic step leaves a culled ray's values un-blanked
-                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, i, out);
+                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, i, out_rows, planes_out, out);
                 if (act & 8) reduce_sample(P.red, out, tally);
             }
             cur = after;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
         }
         if (!GENERAL) {
             if (dead) set_nan(cur);
-            store_ray(P.out, i, cur);
+            store_ray(P.out, i, out_rows, planes_out, cur);
         }
     }
     if (GENERAL && reducing) tally_flush(P.red, tally);
@@ -192,7 +194,7 @@ cudaError_t launch_trace_f64(const TraceParams &P, int sm_count, cudaStream_t st
     if (blocks > max_blocks) blocks = max_blocks;
     const bool table = P.n_wl > 0;
     const bool source = P.src.kind >= 0;
-    const bool fast = P.store_last_only && P.red.slab < 0 && P.flags == 0;
+    const bool fast = P.store_last_only && P.red.slab < 0 && (P.flags & RTB_FLAG_INTERSECT_ONLY) == 0;
     const unsigned b = (unsigned)blocks;
     if (fast) {
         if (table) return source ? launch_one<true, true, 0>(P, b, stream) : launch_one<true, false, 0>(P, b, stream);

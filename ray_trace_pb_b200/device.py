@@ -30,13 +30,16 @@ def _stream_ptr(device_index: int) -> int:
     return _torch().cuda.current_stream(device_index).cuda_stream
 
 
-def _check_rays_tensor(t, what="rays"):
+def _check_rays_tensor(t, what="rays", planes=False):
     torch = _torch()
     if not (isinstance(t, torch.Tensor) and t.is_cuda):
         raise TypeError(f"{what} must be a CUDA torch.Tensor")
     if t.dtype != torch.float64:
         raise TypeError(f"{what} must be float64, got {t.dtype}")
-    if t.dim() != 2 or t.shape[1] != 8:
+    if planes:
+        if t.dim() != 2 or t.shape[0] != 8:
+            raise ValueError(f"{what} must have shape (8, N) in the plane layout, got {tuple(t.shape)}")
+    elif t.dim() != 2 or t.shape[1] != 8:
         raise ValueError(f"{what} must have shape (N, 8), got {tuple(t.shape)}")
     return t.contiguous()
 
@@ -70,31 +73,43 @@ def _system_for(surfaces, materials, wavelengths):
 
 
 def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelengths="auto", reducer=None,
-                 out=None, flags: int = 0):
+                 out=None, flags: int = 0, layout: str = "rows"):
     """
     rays: (N, 8) float64 CUDA tensor; ``materials`` = [initial] + system.materials + [final].
     wavelengths: "auto" scans the batch on the device for its distinct wavelengths (one extra pass over column 7);
     pass the known values (e.g. ``[0.785]``) to skip that, or None to force in-kernel Sellmeier evaluation.
-    Returns a (n_slabs, N, 8) CUDA tensor on the same device (None for keep="none").  Enqueued on the current stream.
+    layout: "rows" = the reference's (N, 8) in, (n_slabs, N, 8) out; "planes" = structure-of-arrays, (8, N) in and
+    (n_slabs, 8, N) out (one contiguous plane per column; give ``wavelengths`` explicitly or it is scanned from a
+    row-major copy of the wavelength plane).
+    Returns a CUDA tensor on the same device (None for keep="none").  Enqueued on the current stream.
     """
     torch = _torch()
-    rays = _check_rays_tensor(rays)
+    if layout not in ("rows", "planes"):
+        raise ValueError("layout must be 'rows' or 'planes'")
+    planes = layout == "planes"
+    rays = _check_rays_tensor(rays, planes=planes)
     dev = rays.device.index
     if isinstance(wavelengths, str):
         if wavelengths != "auto":
             raise ValueError("wavelengths must be 'auto', None or a sequence of values")
-        wavelengths = distinct_wavelengths_tensor(rays)
+        if planes:
+            probe = torch.zeros((rays.shape[1], 8), dtype=torch.float64, device=rays.device)
+            probe[:, 7] = rays[7]
+            wavelengths = distinct_wavelengths_tensor(probe)
+        else:
+            wavelengths = distinct_wavelengths_tensor(rays)
     packed = _system_for(surfaces, materials, wavelengths)
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
     opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
-    opts.flags = flags
-    n = rays.shape[0]
+    opts.flags = flags | ((_ffi.FLAG_PLANES_IN | _ffi.FLAG_PLANES_OUT) if planes else 0)
+    n = rays.shape[1] if planes else rays.shape[0]
+    out_shape = (n_out, 8, n) if planes else (n_out, n, 8)
     if n_out == 0:
         out = None
     elif out is None:
-        out = torch.empty((n_out, n, 8), dtype=torch.float64, device=rays.device)
-    elif tuple(out.shape) != (n_out, n, 8) or out.dtype != torch.float64 or not out.is_contiguous():
-        raise ValueError(f"out must be a contiguous float64 tensor of shape {(n_out, n, 8)}")
+        out = torch.empty(out_shape, dtype=torch.float64, device=rays.device)
+    elif tuple(out.shape) != out_shape or out.dtype != torch.float64 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float64 tensor of shape {out_shape}")
     rc = _ffi.lib().rtb_trace_device(C.byref(packed.sys), rays.data_ptr(), n, out.data_ptr() if out is not None else None,
                                      C.byref(opts), dev, _stream_ptr(dev))
     _ffi.check(rc)

@@ -301,6 +301,24 @@ def test_tensor_api_matches_host_api(rt, rtm, torch, dev):
         dev.trace_tensor(system.surfaces, [m_in] + system.materials + [m_out], torch.zeros((4, 8), device="cuda"))
 
 
+def test_plane_layout_equals_row_layout(rt, rtm, torch, dev):
+    """structure-of-arrays I/O ((8, N) in, (n_slabs, 8, N) out) carries the same bits as the (N, 8) rows"""
+    system, m_in, m_out, rays = systems.edge_mix(rt, rtm)
+    mats = [m_in] + system.materials + [m_out]
+    rows = torch.from_numpy(rays).cuda()
+    planes = rows.t().contiguous()
+    for keep in ("all", "last", [0, 3, 8]):
+        a = dev.trace_tensor(system.surfaces, mats, rows, keep=keep)
+        b = dev.trace_tensor(system.surfaces, mats, planes, keep=keep, layout="planes")
+        assert tuple(b.shape) == (a.shape[0], 8, a.shape[1])
+        parity.assert_bit_identical(b.permute(0, 2, 1).contiguous().cpu().numpy(), a.cpu().numpy(), f"planes, keep={keep}")
+    c = dev.trace_tensor(system.surfaces, mats, planes, keep="last", layout="planes", precision="f32")
+    d = dev.trace_tensor(system.surfaces, mats, rows, keep="last", precision="f32")
+    parity.assert_bit_identical(c.permute(0, 2, 1).contiguous().cpu().numpy(), d.cpu().numpy(), "planes, f32")
+    with pytest.raises(ValueError):
+        dev.trace_tensor(system.surfaces, mats, rows, layout="planes")
+
+
 @pytest.mark.parametrize("kind", ["fan", "collimated", "grid"])
 def test_sources_generate_and_fused_trace(kind, rt, rtm, oracle, dev):
     system = systems.relay10_system(rt, rtm)

@@ -18,11 +18,14 @@ ap.add_argument("--launches", type=int, default=4)
 ap.add_argument("--keep", default="last")
 ap.add_argument("--reduce", default="none")
 ap.add_argument("--precision", default="f64")
+ap.add_argument("--layout", default="rows")
 args = ap.parse_args()
 
 system, materials = bench.relay_system()
 source, side = bench.beam_source(int(args.rays))
 rays = source.generate()
+if args.layout == "planes":
+    rays = rays.t().contiguous()
 reducer = None
 if args.reduce != "none":
     reducer = dev.Reducer(12, origin=(8.0, 0, 0), grid_n=2048 if args.reduce == "grid" else 0, half_width=8.0)
@@ -30,9 +33,9 @@ ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.launches + 1)]
 ev[0].record()
 for i in range(args.launches):
     out = dev.trace_tensor(system.surfaces, materials, rays, keep=args.keep, wavelengths=[bench.WAVELENGTH],
-                           reducer=reducer, precision=args.precision)
+                           reducer=reducer, precision=args.precision, layout=args.layout)
     ev[i + 1].record()
 torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.launches)]
-n = rays.shape[0]
+n = rays.shape[1] if args.layout == "planes" else rays.shape[0]
 print(f"rays {n}  ms/launch {['%.3f' % m for m in ms]}  best {n * 10 / min(ms) / 1e-3 / 1e9:.2f} G ray*surf/s")
