@@ -1,0 +1,78 @@
+"""
+Workload-level helpers built on the fused source -> trace -> reduction kernels: the analyses the reference's example
+scripts do after ``ray_trace`` (spot diagrams, centroids, RMS radii, pupil-phase maps, PSFs), without ever
+materialising the rays.  Everything numerical runs in the kernels of librtb.so; this module only loops over
+sources / fields / wavelengths and collects the small reduced results.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import device as dev
+
+
+def _materials(system, initial_material, final_material):
+    return [initial_material] + list(system.materials) + [final_material]
+
+
+def spot_statistics(system, initial_material, final_material, sources, slab: int = -2, origin=None,
+                    e1=(1.0, 0.0, 0.0), e2=(0.0, 1.0, 0.0), precision: str = "f64", device: int = 0,
+                    chunk: int = 1 << 27):
+    """
+    Spot statistics of one or several ray bundles at slab ``slab`` (default: at the last surface, the scripts'
+    ``rays[-2]``): for each :class:`~ray_trace_pb_b200.device.RaySource` a dict with ``count``, ``centroid``,
+    ``rms_radius``, ``mean_phase``, ``rms_phase``, ``u_range``, ``v_range``.  ``origin`` defaults to the centre of the
+    surface the slab belongs to.  One fused kernel launch per source chunk; no ray I/O.
+    """
+    single = isinstance(sources, dev.RaySource)
+    sources = [sources] if single else list(sources)
+    n_slabs = 2 * len(system.surfaces) + 1
+    slab = slab + n_slabs if slab < 0 else slab
+    if origin is None:
+        origin = system.surfaces[max(slab - 1, 0) // 2].center
+    mats = _materials(system, initial_material, final_material)
+    results = []
+    for src in sources:
+        red = dev.Reducer(slab, origin=origin, e1=e1, e2=e2, device=device)
+        for first in range(0, src.n_rays, chunk):
+            count = min(chunk, src.n_rays - first)
+            dev.trace_source(system.surfaces, mats, src, first=first, count=count, keep="none", precision=precision,
+                             reducer=red, device=device)
+        results.append(red.stats())
+    return results[0] if single else results
+
+
+def pupil_grid(system, initial_material, final_material, source, slab: int, origin, e1, e2, grid_n: int,
+               half_width: float, phase_ref: float = 0.0, precision: str = "f64", device: int = 0,
+               chunk: int = 1 << 27):
+    """
+    Accumulate sum cos / sum sin / count of the phase of ``source``'s rays at slab ``slab`` on a ``grid_n`` x ``grid_n``
+    grid spanning ``[-half_width, half_width)`` in the plane basis ``(origin, e1, e2)``.  Returns the
+    :class:`~ray_trace_pb_b200.device.Reducer` (``.grid``, ``.stats()``, ``.psf()``, ``.allreduce()``).
+    """
+    n_slabs = 2 * len(system.surfaces) + 1
+    slab = slab + n_slabs if slab < 0 else slab
+    mats = _materials(system, initial_material, final_material)
+    red = dev.Reducer(slab, origin=origin, e1=e1, e2=e2, grid_n=grid_n, half_width=half_width, phase_ref=phase_ref,
+                      device=device)
+    for first in range(0, source.n_rays, chunk):
+        count = min(chunk, source.n_rays - first)
+        dev.trace_source(system.surfaces, mats, source, first=first, count=count, keep="none", precision=precision,
+                         reducer=red, device=device)
+    return red
+
+
+def axial_crossing(system, initial_material, final_material, wavelength: float, height: float, n_phi: int = 64,
+                   pt=(0.0, 0.0, 0.0), normal=(0.0, 0.0, 1.0), device: int = 0):
+    """
+    Where a ring of collimated rays at radial ``height`` crosses the axis ray behind the system (mean over the ring):
+    the quantity behind the scripts' longitudinal-spherical-aberration and chromatic-focal-shift curves
+    (``intersect_rays(axis_ray, rays[-1])``, e.g. scripts/2022_08_04_ACT508-100-B.py:158).  Returns a 3-vector.
+    """
+    from .raytrace import get_collimated_rays, intersect_rays
+    ring = get_collimated_rays(pt, height, 2, wavelength, nphis=n_phi, normal=normal)[n_phi:]   # offsets = +height
+    axis = get_collimated_rays(pt, 0.0, 1, wavelength, normal=normal)
+    traced = system.ray_trace(np.concatenate((axis, ring)), initial_material, final_material, keep="last",
+                              device=device)[0]
+    pts = intersect_rays(traced[0], traced[1:])
+    return np.nanmean(pts, axis=0)
