@@ -62,17 +62,17 @@ def pupil_grid(system, initial_material, final_material, source, slab: int, orig
     return red
 
 
-def axial_crossing(system, initial_material, final_material, wavelength: float, height: float, n_phi: int = 64,
+def axial_crossing(system, initial_material, final_material, wavelength: float, height: float,
                    pt=(0.0, 0.0, 0.0), normal=(0.0, 0.0, 1.0), device: int = 0):
     """
-    Where a ring of collimated rays at radial ``height`` crosses the axis ray behind the system (mean over the ring):
-    the quantity behind the scripts' longitudinal-spherical-aberration and chromatic-focal-shift curves
-    (``intersect_rays(axis_ray, rays[-1])``, e.g. scripts/2022_08_04_ACT508-100-B.py:158).  Returns a 3-vector.
+    Where the two meridional rays launched parallel to ``normal`` at ``+-height`` (along the bundle's first
+    transverse axis) cross the centre ray behind the system (mean of the two crossings): the quantity behind the
+    scripts' longitudinal-spherical-aberration and chromatic-focal-shift curves (``intersect_rays(axis_ray,
+    rays[-1])``, e.g. scripts/2022_08_04_ACT508-100-B.py:158).  Returns a 3-vector (NaN where the rays do not meet
+    to within the reference's 1e-12, as there).
     """
     from .raytrace import get_collimated_rays, intersect_rays
-    ring = get_collimated_rays(pt, height, 2, wavelength, nphis=n_phi, normal=normal)[n_phi:]   # offsets = +height
-    axis = get_collimated_rays(pt, 0.0, 1, wavelength, normal=normal)
-    traced = system.ray_trace(np.concatenate((axis, ring)), initial_material, final_material, keep="last",
-                              device=device)[0]
-    pts = intersect_rays(traced[0], traced[1:])
+    probe = get_collimated_rays(pt, height, 3, wavelength, normal=normal)       # offsets -h, 0, +h in one plane
+    traced = system.ray_trace(probe, initial_material, final_material, keep="last", device=device)[0]
+    pts = intersect_rays(traced[1], traced[[0, 2]])
     return np.nanmean(pts, axis=0)
