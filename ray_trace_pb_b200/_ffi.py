@@ -158,10 +158,62 @@ def require_device() -> int:
     return n
 
 
-def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
-    """A NumPy array in page-locked memory (freed when the array is garbage collected)."""
+class _PinnedPool:
+    """
+    Page-locked host buffers recycled across calls.  Pinning memory costs ~0.45 s/GiB and a fresh pageable result
+    array costs a page fault per 4 KiB, which is what bounds a drop-in ``System.ray_trace`` returning a GiB-sized
+    history; a recycled pinned buffer is written by DMA at PCIe speed instead.  Buffers return to the pool when the
+    NumPy arrays viewing them are garbage collected.  RTB_PINNED_POOL_GB caps the idle bytes kept (default 8).
+    """
+
+    GRANULE = 32 << 20
+
+    def __init__(self):
+        self.free = {}          # rounded size -> [ptr, ...]
+        self.idle_bytes = 0
+        self.cap = int(float(os.environ.get("RTB_PINNED_POOL_GB", "8")) * (1 << 30))
+
+    def take(self, nbytes: int):
+        size = max(self.GRANULE, -(-nbytes // self.GRANULE) * self.GRANULE)
+        bucket = self.free.get(size)
+        if bucket:
+            self.idle_bytes -= size
+            return bucket.pop(), size
+        ptr = lib().rtb_host_alloc(size)
+        if not ptr:
+            self.trim(0)
+            ptr = lib().rtb_host_alloc(size)
+            if not ptr:
+                check(RTB_ERR_NOMEM)
+        return ptr, size
+
+    def give(self, ptr, size):
+        if self.idle_bytes + size > self.cap:
+            _free_pinned(ptr)
+            return
+        self.free.setdefault(size, []).append(ptr)
+        self.idle_bytes += size
+
+    def trim(self, keep_bytes: int = 0):
+        for size, bucket in list(self.free.items()):
+            while bucket and self.idle_bytes > keep_bytes:
+                _free_pinned(bucket.pop())
+                self.idle_bytes -= size
+
+
+_pool = _PinnedPool()
+
+
+def pinned_empty(shape, dtype=np.float64, pooled: bool = False) -> np.ndarray:
+    """A NumPy array in page-locked memory (released -- or returned to the pool -- when it is garbage collected)."""
     dtype = np.dtype(dtype)
-    nbytes = int(np.prod(shape)) * dtype.itemsize
+    count = int(np.prod(shape))
+    nbytes = count * dtype.itemsize
+    if pooled:
+        ptr, size = _pool.take(max(nbytes, 1))
+        buf = (C.c_char * size).from_address(ptr)
+        weakref.finalize(buf, _pool.give, ptr, size)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
     ptr = lib().rtb_host_alloc(max(nbytes, 1))
     if not ptr:
         check(RTB_ERR_NOMEM)
@@ -169,7 +221,15 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     # every view of the returned array reaches `buf` through its .base chain, so the allocation lives as long as
     # any of them does
     weakref.finalize(buf, _free_pinned, ptr)
-    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+def result_array(shape) -> np.ndarray:
+    """Where a host-path trace puts its result: recycled pinned memory for big histories, plain NumPy for small."""
+    nbytes = int(np.prod(shape)) * 8
+    if nbytes >= (8 << 20):
+        return pinned_empty(shape, pooled=True)
+    return np.empty(shape, dtype=np.float64)
 
 
 def _free_pinned(ptr):

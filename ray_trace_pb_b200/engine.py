@@ -245,7 +245,7 @@ def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64
     mode, idx, n_out = resolve_keep(keep, packed.n_slabs)
     opts = make_opts(mode, idx, precision, reduce)
     if out is None:
-        out = np.empty((n_out, n, 8), dtype=np.float64)
+        out = _ffi.result_array((n_out, n, 8))
     elif out.shape != (n_out, n, 8) or out.dtype != np.float64 or not out.flags.c_contiguous:
         raise ValueError(f"out must be a C-contiguous float64 array of shape {(n_out, n, 8)}")
     rc = _ffi.lib().rtb_trace_host(C.byref(packed.sys), rays.ctypes.data, n, out.ctypes.data if n_out else None,

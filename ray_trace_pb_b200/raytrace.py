@@ -215,7 +215,7 @@ class System:
         prior, launch = rays[:-1], rays[-1]
         if isinstance(keep, str) and keep == "all":
             n_new = 2 * len(self.surfaces) + 1
-            out = np.empty((prior.shape[0] + n_new, launch.shape[0], 8), dtype=np.float64)
+            out = _ffi.result_array((prior.shape[0] + n_new, launch.shape[0], 8))
             out[:prior.shape[0]] = prior
             engine.trace_host(self.surfaces, materials, launch, keep="all", precision=precision, device=device,
                               out=out[prior.shape[0]:])
