@@ -149,52 +149,6 @@ __device__ __forceinline__ void fill_at_f(bool kill, double px, double py, doubl
     if (kill) set_nan(at);
 }
 
-// flat / sphere refraction and plane mirror (raytrace.py:1160-1303)
-__device__ __forceinline__ bool bend_step(const DevSurface &s, const RayM &in, double k, double n1, double ratio,
-                                          float inv_radius, bool front_cull, RayM &at, RayM &after)
-{
-    const SurfF f = surf_f32(s, inv_radius);
-    double px, py, pz, ph;
-    float nx, ny, nz;
-    bool kill = false, on;
-    if (s.kind == RTB_SURF_SPHERE) {
-        // quadratic in fp64 (raytrace.py:1497-1509), root in fp32
-        const double qx = in.ox - s.cx, qy = in.oy - s.cy, qz = in.oz - s.cz;
-        const double b = fma((double)in.dz, qz, fma((double)in.dy, qy, (double)in.dx * qx));
-        const double cq = fma(qz, qz, fma(qy, qy, qx * qx)) - s.radius_sq;
-        const double root = (double)sqrtf((float)fma(b, b, -cq));
-        const double t1 = root - b, t2 = -b - root;
-        double t = (t2 < 0.0) ? t1 : t2;
-        t = (t1 < 0.0 || root != root) ? CUDART_NAN : t;
-        px = fma((double)in.dx, t, in.ox);
-        py = fma((double)in.dy, t, in.oy);
-        pz = fma((double)in.dz, t, in.oz);
-        ph = fma(t, k * n1, in.ph);
-        nx = (float)(px - s.cx) * f.inv_radius;
-        ny = (float)(py - s.cy) * f.inv_radius;
-        nz = (float)(pz - s.cz) * f.inv_radius;
-        // aperture measured from the axis through the origin (raytrace.py:1530-1533)
-        const float fx = (float)px, fy = (float)py, fz = (float)pz;
-        const float along = dot3f(fx, fy, fz, f.ax, f.ay, f.az);
-        const float ux = fmaf(-along, f.ax, fx), uy = fmaf(-along, f.ay, fy), uz = fmaf(-along, f.az, fz);
-        on = dot3f(ux, uy, uz, ux, uy, uz) <= f.aperture_sq;
-    } else {
-        const float t = to_plane_f(in, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n1, px, py, pz, ph);
-        kill = t < 0.0f;
-        nx = f.nx; ny = f.ny; nz = f.nz;
-        const float rx = (float)(px - s.cx), ry = (float)(py - s.cy), rz = (float)(pz - s.cz);
-        on = dot3f(rx, ry, rz, rx, ry, rz) <= f.aperture_sq;
-    }
-    const bool mirror = s.kind == RTB_SURF_MIRROR;
-    if (front_cull && !mirror) kill = kill || (dot3f(in.dx, in.dy, in.dz, f.ax, f.ay, f.az) < 0.0f);
-    on = on && !kill;
-    float ex, ey, ez;
-    bend(in.dx, in.dy, in.dz, nx, ny, nz, (float)ratio, mirror, ex, ey, ez);
-    finish(on, px, py, pz, ex, ey, ez, ph, in.wl, after);
-    fill_at_f(kill, px, py, pz, ph, in, at);
-    return !on;
-}
-
 // PerfectLens.propagate (raytrace.py:1601-1801)
 __device__ __forceinline__ bool lens_step(const DevSurface &s, const RayM &in, double k, double n1, double n2,
                                           bool as_get_intersect, RayM &before, RayM &after)
@@ -277,8 +231,14 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
             first = make_ray(P.src, P.src.first + i);
         else
             load_ray(P.rays_in, i, P.n_rays, planes_in, first);
-        RayM cur = narrow(first);
-        const double wl0 = cur.wl;
+        if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, i, out_rows, planes_out, first);
+        if (reducing && P.red.slab == 0) reduce_sample(P.red, first, tally);
+
+        // the ray, in registers: position / phase fp64, direction fp32; the wavelength only ever turns NaN with the
+        // whole ray (dead)
+        double ox = first.ox, oy = first.oy, oz = first.oz, ph = first.ph;
+        float dx = (float)first.dx, dy = (float)first.dy, dz = (float)first.dz;
+        const double wl0 = first.wl;
         const double k = kTwoPi / wl0;
         int row = 0;
         bool unlisted = false;
@@ -291,38 +251,105 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
             unlisted = (row == P.n_wl) && (wl0 == wl0);
             row *= n_med;
         }
-        if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, i, out_rows, planes_out, first);
-        if (reducing && P.red.slab == 0) reduce_sample(P.red, first, tally);
-
         double n1 = !USE_TABLE ? eval_index(P.mat[0], wl0) : (unlisted ? index_for_unlisted(&P.mat[0], wl0) : s_ntab[row]);
-        bool dead = false;
+        bool dead = false;           // every column NaN from here on
 #pragma unroll 1
         for (int q = 0; q < P.n_surf; q++) {
             const DevSurface &s = P.surf[q];
             const double n2 = !USE_TABLE ? eval_index(P.mat[q + 1], wl0)
                                          : (unlisted ? index_for_unlisted(&P.mat[q + 1], wl0) : s_ntab[row + q + 1]);
             const int act = P.slab_act[q];
-            RayM at, after;
+            auto emit = [&](bool at_slab, const Ray &w) {
+                const int pos = P.slab_pos[2 * q + (at_slab ? 1 : 2)];
+                if (act & (at_slab ? 1 : 2)) store_ray(P.out + pos * P.out_stride, i, out_rows, planes_out, w);
+                if (act & (at_slab ? 4 : 8)) reduce_sample(P.red, w, tally);
+            };
             if (dead) {
-                set_nan(at);
-                set_nan(after);
+                if (act) {
+                    Ray w;
+                    set_nan(w);
+                    if (act & 5) emit(true, w);
+                    if (act & 10) emit(false, w);
+                }
             } else if (s.kind == RTB_SURF_PERFECT_LENS) {
+                RayM cur, at, after;
+                cur.ox = ox; cur.oy = oy; cur.oz = oz; cur.dx = dx; cur.dy = dy; cur.dz = dz; cur.ph = ph;
+                cur.wl = wl0;
                 dead = lens_step(s, cur, k, n1, n2, intersect_only, at, after);
+                if (act & 5) emit(true, widen(at));
+                if (act & 10) emit(false, widen(after));
+                ox = after.ox; oy = after.oy; oz = after.oz; dx = after.dx; dy = after.dy; dz = after.dz; ph = after.ph;
             } else {
+                // ---- flat / sphere refraction and plane mirror (raytrace.py:1160-1303) ----
+                const bool mirror = s.kind == RTB_SURF_MIRROR;
+                const double ddx = (double)dx, ddy = (double)dy, ddz = (double)dz;
+                const float snx = (float)s.nx, sny = (float)s.ny, snz = (float)s.nz;
+                double px, py, pz, ph_at;
+                float nx, ny, nz;
+                bool kill = false, on;
+                if (s.kind == RTB_SURF_SPHERE) {
+                    // quadratic in fp64 (raytrace.py:1497-1509), root in fp32
+                    const double qx = ox - s.cx, qy = oy - s.cy, qz = oz - s.cz;
+                    const double b = fma(ddz, qz, fma(ddy, qy, ddx * qx));
+                    const double cq = fma(qz, qz, fma(qy, qy, qx * qx)) - s.radius_sq;
+                    const double root = (double)sqrtf((float)fma(b, b, -cq));
+                    const double t1 = root - b, t2 = -b - root;
+                    double t = (t2 < 0.0) ? t1 : t2;
+                    t = (t1 < 0.0 || root != root) ? CUDART_NAN : t;
+                    px = fma(ddx, t, ox);
+                    py = fma(ddy, t, oy);
+                    pz = fma(ddz, t, oz);
+                    ph_at = fma(t, k * n1, ph);
+                    const float inv_r = s_inv_radius[q];
+                    nx = (float)(px - s.cx) * inv_r;
+                    ny = (float)(py - s.cy) * inv_r;
+                    nz = (float)(pz - s.cz) * inv_r;
+                    // aperture measured from the axis through the origin (raytrace.py:1530-1533); fp64 is cheaper
+                    // here than three more conversions
+                    const double along = fma(pz, s.az, fma(py, s.ay, px * s.ax));
+                    const double ux = fma(-along, s.ax, px), uy = fma(-along, s.ay, py), uz = fma(-along, s.az, pz);
+                    on = fma(uz, uz, fma(uy, uy, ux * ux)) <= s.aperture * s.aperture;
+                } else {
+                    const float rx = (float)(ox - s.cx), ry = (float)(oy - s.cy), rz = (float)(oz - s.cz);
+                    const float t = -dot3f(rx, ry, rz, snx, sny, snz) / dot3f(dx, dy, dz, snx, sny, snz);
+                    const double td = (double)t;
+                    px = fma(ddx, td, ox);
+                    py = fma(ddy, td, oy);
+                    pz = fma(ddz, td, oz);
+                    ph_at = fma(td, k * n1, ph);
+                    kill = t < 0.0f;
+                    nx = snx; ny = sny; nz = snz;
+                    const double ux = px - s.cx, uy = py - s.cy, uz = pz - s.cz;
+                    on = fma(uz, uz, fma(uy, uy, ux * ux)) <= s.aperture * s.aperture;
+                }
+                if (!intersect_only && !mirror)
+                    kill = kill || (dot3f(dx, dy, dz, (float)s.ax, (float)s.ay, (float)s.az) < 0.0f);
+                on = on && !kill;
+                if (act & 5) {
+                    Ray w;
+                    w.ox = px; w.oy = py; w.oz = pz; w.dx = ddx; w.dy = ddy; w.dz = ddz; w.ph = ph_at;
+                    w.wl = wl0;
+                    if (kill) set_nan(w);
+                    emit(true, w);
+                }
                 const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + q] : n1 / n2;
-                dead = bend_step(s, cur, k, n1, ratio, s_inv_radius[q], !intersect_only, at, after);
+                float ex, ey, ez;
+                bend(dx, dy, dz, nx, ny, nz, (float)ratio, mirror, ex, ey, ez);
+                dead = !on;
+                const bool no_dir = ex != ex;             // beyond the critical angle: position blanked too
+                ox = no_dir ? CUDART_NAN : px;
+                oy = no_dir ? CUDART_NAN : py;
+                oz = no_dir ? CUDART_NAN : pz;
+                dx = ex; dy = ey; dz = ez;
+                ph = ph_at;
+                if (act & 10) {
+                    Ray w;
+                    w.ox = ox; w.oy = oy; w.oz = oz; w.dx = (double)ex; w.dy = (double)ey; w.dz = (double)ez; w.ph = ph;
+                    w.wl = wl0;
+                    if (dead) set_nan(w);
+                    emit(false, w);
+                }
             }
-            if (act & 5) {
-                const Ray w = widen(at);
-                if (act & 1) store_ray(P.out + P.slab_pos[2 * q + 1] * P.out_stride, i, out_rows, planes_out, w);
-                if (act & 4) reduce_sample(P.red, w, tally);
-            }
-            if (act & 10) {
-                const Ray w = widen(after);
-                if (act & 2) store_ray(P.out + P.slab_pos[2 * q + 2] * P.out_stride, i, out_rows, planes_out, w);
-                if (act & 8) reduce_sample(P.red, w, tally);
-            }
-            cur = after;
             n1 = n2;
         }
     }
