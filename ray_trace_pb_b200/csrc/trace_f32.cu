@@ -206,16 +206,26 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
 {
     __shared__ double s_ntab[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     __shared__ double s_ratio[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
-    __shared__ float s_inv_radius[kMaxSurfaces];
+    // per-surface fp32 constants and the fp32 copy of n1/n2, converted once per block (conversions run on the
+    // quarter-rate XU pipe, so they must not be repeated per ray)
+    __shared__ float s_geo[kMaxSurfaces][8];   // normal xyz, axis xyz, 1/R, aperture^2 (unused slot)
+    __shared__ float s_ratio_f[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     const int n_med = P.n_surf + 1;
     if (USE_TABLE) {
         const int count = (P.n_wl + 1) * n_med;
         for (int k = threadIdx.x; k < count; k += blockDim.x) {
             s_ntab[k] = P.n_tab[k];
             s_ratio[k] = P.ratio_tab[k];
+            s_ratio_f[k] = (float)P.ratio_tab[k];
         }
     }
-    for (int k = threadIdx.x; k < P.n_surf; k += blockDim.x) s_inv_radius[k] = (float)(1.0 / P.surf[k].radius);
+    for (int k = threadIdx.x; k < P.n_surf; k += blockDim.x) {
+        const DevSurface &s = P.surf[k];
+        s_geo[k][0] = (float)s.nx; s_geo[k][1] = (float)s.ny; s_geo[k][2] = (float)s.nz;
+        s_geo[k][3] = (float)s.ax; s_geo[k][4] = (float)s.ay; s_geo[k][5] = (float)s.az;
+        s_geo[k][6] = (float)(1.0 / s.radius);
+        s_geo[k][7] = 0.0f;
+    }
     __syncthreads();
     const bool reducing = P.red.slab >= 0;
     const bool intersect_only = (P.flags & RTB_FLAG_INTERSECT_ONLY) != 0;
@@ -283,7 +293,7 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                 // ---- flat / sphere refraction and plane mirror (raytrace.py:1160-1303) ----
                 const bool mirror = s.kind == RTB_SURF_MIRROR;
                 const double ddx = (double)dx, ddy = (double)dy, ddz = (double)dz;
-                const float snx = (float)s.nx, sny = (float)s.ny, snz = (float)s.nz;
+                const float snx = s_geo[q][0], sny = s_geo[q][1], snz = s_geo[q][2];
                 double px, py, pz, ph_at;
                 float nx, ny, nz;
                 bool kill = false, on;
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                     py = fma(ddy, t, oy);
                     pz = fma(ddz, t, oz);
                     ph_at = fma(t, k * n1, ph);
-                    const float inv_r = s_inv_radius[q];
+                    const float inv_r = s_geo[q][6];
                     nx = (float)(px - s.cx) * inv_r;
                     ny = (float)(py - s.cy) * inv_r;
                     nz = (float)(pz - s.cz) * inv_r;
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                     on = fma(uz, uz, fma(uy, uy, ux * ux)) <= s.aperture * s.aperture;
                 }
                 if (!intersect_only && !mirror)
-                    kill = kill || (dot3f(dx, dy, dz, (float)s.ax, (float)s.ay, (float)s.az) < 0.0f);
+                    kill = kill || (dot3f(dx, dy, dz, s_geo[q][3], s_geo[q][4], s_geo[q][5]) < 0.0f);
                 on = on && !kill;
                 if (act & 5) {
                     Ray w;
@@ -332,9 +342,9 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                     if (kill) set_nan(w);
                     emit(true, w);
                 }
-                const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + q] : n1 / n2;
+                const float ratio = (USE_TABLE && !unlisted) ? s_ratio_f[row + q] : (float)(n1 / n2);
                 float ex, ey, ez;
-                bend(dx, dy, dz, nx, ny, nz, (float)ratio, mirror, ex, ey, ez);
+                bend(dx, dy, dz, nx, ny, nz, ratio, mirror, ex, ey, ez);
                 dead = !on;
                 const bool no_dir = ex != ex;             // beyond the critical angle: position blanked too
                 ox = no_dir ? CUDART_NAN : px;
