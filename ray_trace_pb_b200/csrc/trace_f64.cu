@@ -100,9 +100,12 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
 
         double n1 = !USE_TABLE ? eval_index(P.mat[0], wl0)
                                : (unlisted ? index_for_unlisted(&P.mat[0], wl0) : s_ntab[row]);
+        // Live rays run the surface loop; a ray that dies (leaves a surface all-NaN) drops out of it and only has
+        // its remaining slabs blanked below -- an all-NaN ray stays all-NaN through every kind of surface.
         bool dead = false;
+        int k = 0;
 #pragma unroll 1
-        for (int k = 0; k < P.n_surf; k++) {
+        for (; k < P.n_surf && !dead; k++) {
             const DevSurface &s = P.surf[k];
             const double n2 = !USE_TABLE ? eval_index(P.mat[k + 1], wl0)
                                          : (unlisted ? index_for_unlisted(&P.mat[k + 1], wl0) : s_ntab[row + k + 1]);
@@ -110,53 +113,55 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             // 2 reduce "at", 3 reduce "after"
             const int act = GENERAL ? P.slab_act[k] : 0;
             const bool need_at = (act & 5) != 0;
-            Ray after;
             auto emit_at = [&](const Ray &at) {
                 if (act & 1) store_ray(P.out + P.slab_pos[2 * k + 1] * P.out_stride, i, out_rows, planes_out, at);
                 if (act & 4) reduce_sample(P.red, at, tally);
             };
-            if (dead) {
-                // an all-NaN ray stays all-NaN through every kind of surface: skip the arithmetic
-                set_nan(after);
-                if (need_at) emit_at(after);
-            } else {
-                xm::Rcp rcp_k;
-                rcp_k.b = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
-                rcp_k.y = s_c.rcp_radius[k];
-                rcp_k.ok = (s_c.rcp_ok >> k) & 1ull;
-                // run the surface optimistically; one flag says whether every intermediate stayed in the fast
-                // paths' domain, otherwise redo this surface with the Careful arithmetic (surface_steps.cuh)
-                Optimistic m;
-                AtRaw raw;
-                StepResult redo;
-                if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {
-                    const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + k] : xm::div(n1, n2);
-                    // two instantiations so that the at-surface values are only kept alive where they are consumed
-                    dead = need_at ? refracting_step<Optimistic, true>(m, s, cur, n1, ratio, rcp_wl, rcp_k,
-                                                                       !intersect_only, raw, after)
-                                   : refracting_step<Optimistic, false>(m, s, cur, n1, ratio, rcp_wl, rcp_k,
-                                                                        !intersect_only, raw, after);
-                    if (!m.ok) redo = careful_refracting(&s, cur, n1, ratio, !intersect_only);
-                } else if (s.kind == RTB_SURF_MIRROR) {
-                    dead = need_at ? mirror_step<Optimistic, true>(m, s, cur, n1, rcp_wl, raw, after)
-                                   : mirror_step<Optimistic, false>(m, s, cur, n1, rcp_wl, raw, after);
-                    if (!m.ok) redo = careful_mirror(&s, cur, n1);
-                } else {
-                    dead = perfect_lens_step<Optimistic>(m, s, cur, n1, n2, rcp_wl, rcp_k, intersect_only, need_at, raw,
-                                                         after);
-                    if (!m.ok) redo = careful_lens(&s, cur, n1, n2, intersect_only);
-                }
-                if (m.ok) {
-                    if (need_at) {
-                        Ray at;
-                        fill_at(raw, cur, at);
-                        emit_at(at);
-                    }
-                } else {
+            xm::Rcp rcp_k;
+            rcp_k.b = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
+            rcp_k.y = s_c.rcp_radius[k];
+            rcp_k.ok = (s_c.rcp_ok >> k) & 1ull;
+            // run the surface optimistically; one flag says whether every intermediate stayed in the fast
+            // paths' domain, otherwise redo this surface with the Careful arithmetic (surface_steps.cuh)
+            Optimistic m;
+            AtRaw raw;
+            Ray after;
+            if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {
+                const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + k] : xm::div(n1, n2);
+                // two instantiations so that the at-surface values are only kept alive where they are consumed
+                dead = need_at ? refracting_step<Optimistic, true>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only,
+                                                                   raw, after)
+                               : refracting_step<Optimistic, false>(m, s, cur, n1, ratio, rcp_wl, rcp_k,
+                                                                    !intersect_only, raw, after);
+                if (!m.ok) {
+                    const StepResult redo = careful_refracting(&s, cur, n1, ratio, !intersect_only);
                     if (need_at) emit_at(redo.at);
                     after = redo.after;
                     dead = redo.dead;
                 }
+            } else if (s.kind == RTB_SURF_MIRROR) {
+                dead = need_at ? mirror_step<Optimistic, true>(m, s, cur, n1, rcp_wl, raw, after)
+                               : mirror_step<Optimistic, false>(m, s, cur, n1, rcp_wl, raw, after);
+                if (!m.ok) {
+                    const StepResult redo = careful_mirror(&s, cur, n1);
+                    if (need_at) emit_at(redo.at);
+                    after = redo.after;
+                    dead = redo.dead;
+                }
+            } else {
+                dead = perfect_lens_step<Optimistic>(m, s, cur, n1, n2, rcp_wl, rcp_k, intersect_only, need_at, raw,
+                                                     after);
+                if (!m.ok) {
+                    const StepResult redo = careful_lens(&s, cur, n1, n2, intersect_only);
+                    if (need_at) emit_at(redo.at);
+                    after = redo.after;
+                    dead = redo.dead;
+                }
+            }
+            if (m.ok && need_at) {
+                Ray at;
+                fill_at(raw, cur, at);
+                emit_at(at);
             }
             if (GENERAL && (act & 10)) {
                 Ray out = after;
@@ -166,6 +171,17 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             }
             cur = after;
             n1 = n2;
+        }
+        if (GENERAL && dead) {
+            // blank what is left of a dead ray's history (reductions skip NaN samples, nothing to add there)
+            Ray blank;
+            set_nan(blank);
+#pragma unroll 1
+            for (; k < P.n_surf; k++) {
+                const int act = P.slab_act[k];
+                if (act & 1) store_ray(P.out + P.slab_pos[2 * k + 1] * P.out_stride, i, out_rows, planes_out, blank);
+                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, i, out_rows, planes_out, blank);
+            }
         }
         if (!GENERAL) {
             if (dead) set_nan(cur);
