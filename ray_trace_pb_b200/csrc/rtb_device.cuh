@@ -23,7 +23,10 @@ constexpr int kMaxWavelengths = RTB_MAX_WAVELENGTHS;
 constexpr int kMaxSlabs = 2 * RTB_MAX_SURFACES + 1;
 
 // launch shape of the trace kernels: 128-thread blocks, register budget for kTraceMinBlocks resident blocks per SM
-constexpr int kTraceThreads = 128;
+#ifndef RTB_TRACE_THREADS
+#define RTB_TRACE_THREADS 128
+#endif
+constexpr int kTraceThreads = RTB_TRACE_THREADS;
 #ifndef RTB_TRACE_MIN_BLOCKS
 #define RTB_TRACE_MIN_BLOCKS 7
 #endif

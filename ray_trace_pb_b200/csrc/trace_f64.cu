@@ -104,7 +104,11 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
         // its remaining slabs blanked below -- an all-NaN ray stays all-NaN through every kind of surface.
         bool dead = false;
         int k = 0;
+#ifdef RTB_SURFACE_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (; k < P.n_surf && !dead; k++) {
             const DevSurface &s = P.surf[k];
             const double n2 = !USE_TABLE ? eval_index(P.mat[k + 1], wl0)

@@ -479,6 +479,34 @@ def test_psf_airy_known_answer(rt, rtm, dev, torch):
     assert abs(first_min - 3.8317 / (2 * np.pi * r_pupil)) <= df
 
 
+# ------------------------------------------------------------------------------------------------ workload helpers
+def test_analysis_spot_statistics_and_axial_crossing(rt, rtm, oracle, dev):
+    """analysis.spot_statistics (fused source -> trace -> statistics) against NumPy on the oracle's trace"""
+    from ray_trace_pb_b200 import analysis
+    system = systems.relay10_system(rt, rtm)
+    vac = rtm.Vacuum()
+    mats = [vac] + system.materials + [vac]
+    sources = []
+    for th in (0.0, 0.01):
+        nrm = np.array([np.sin(th), 0, np.cos(th)])
+        sources.append(dev.RaySource.grid([0, 0, 0], 12.0, 181, 0.785, normal=nrm / np.linalg.norm(nrm)))
+    got = analysis.spot_statistics(system, vac, vac, sources, slab=-2, chunk=10_000)      # several launches per source
+    for src, g in zip(sources, got):
+        rays = src.generate().cpu().numpy()
+        hist = oracle.trace(system.surfaces, mats, rays, keep_all=True, n_threads=8)
+        want = oracle.reduce_stats(hist[-2], system.surfaces[-1].center, (1, 0, 0), (0, 1, 0))
+        assert g["count"] == int(want[0]) > 30_000
+        np.testing.assert_allclose(g["raw"][1:8], want[1:8], rtol=1e-10, atol=1e-7)
+        p = hist[-2][np.isfinite(hist[-2][:, 0]), 0:2] - system.surfaces[-1].center[0:2]
+        np.testing.assert_allclose(g["centroid"], p.mean(axis=0), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(g["rms_radius"], np.sqrt(((p - p.mean(axis=0)) ** 2).sum(axis=1).mean()), rtol=1e-7)
+    # paraxial focus of a doublet from the crossing of two meridional rays = the cardinal-point back focal point
+    doublet = rt.Doublet(rtm.Nlak22(), rtm.Nsf6ht(), radius_crown=65.8, radius_flint=-280.6, radius_interface=-56,
+                         thickness_crown=13.0, thickness_flint=2.0, aperture_radius=25.4)
+    z = analysis.axial_crossing(doublet, vac, vac, 0.855, 1e-3, pt=(0, 0, -10.0))[2]
+    assert abs(z - doublet.get_cardinal_points(0.855, vac, vac)[1][2]) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 def test_intersect_rays(rt, torch):
     g = load_golden("intersect_rays")

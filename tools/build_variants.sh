@@ -1,14 +1,18 @@
 #!/bin/bash
-# Build librtb_mb<N>.so variants (RTB_TRACE_MIN_BLOCKS = N) for A/B runs on the GPU box (RTB_LIBRARY_PATH selects one).
+# Build librtb_<name>.so variants for A/B runs on the GPU box (RTB_LIBRARY_PATH selects one).
+#   tools/build_variants.sh mb6:-DRTB_TRACE_MIN_BLOCKS=6 u2:"-DRTB_SURFACE_UNROLL2 -DRTB_TRACE_MIN_BLOCKS=7"
+# A bare number N is shorthand for mbN:-DRTB_TRACE_MIN_BLOCKS=N.
 set -e
 cd "$(dirname "$0")/../ray_trace_pb_b200/csrc"
-for mb in "$@"; do
-  mkdir -p ../_lib/var$mb
+for spec in "$@"; do
+  if [[ "$spec" =~ ^[0-9]+$ ]]; then name="mb$spec"; defs="-DRTB_TRACE_MIN_BLOCKS=$spec"; else name="${spec%%:*}"; defs="${spec#*:}"; fi
+  mkdir -p ../_lib/var_$name
   for f in rtb_api trace_f64 trace_f32 aux_kernels psf_kernels; do
-    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v \
-      -DRTB_TRACE_MIN_BLOCKS=$mb -c $f.cu -o ../_lib/var$mb/$f.o 2> ../_lib/var$mb/$f.log &
+    extra="-fmad=false"; [ $f = trace_f32 ] && extra="-fmad=true -prec-div=false -prec-sqrt=false"
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo $extra -Xcompiler -fPIC -Xptxas -v \
+      $defs -c $f.cu -o ../_lib/var_$name/$f.o 2> ../_lib/var_$name/$f.log &
   done
   wait
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../_lib/librtb_mb$mb.so ../_lib/var$mb/*.o
-  echo "mb=$mb: $(grep -A1 'ILb1ELb0ELi0' ../_lib/var$mb/trace_f64.log | grep -E 'spill' | head -1) $(grep 'Used' ../_lib/var$mb/trace_f64.log | sed -n 7p | cut -c1-40)"
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../_lib/librtb_$name.so ../_lib/var_$name/*.o
+  echo "$name: $(grep -A1 'ILb1ELb0ELi0' ../_lib/var_$name/trace_f64.log | grep -E 'spill' | head -1) $(grep -A2 'ILb1ELb0ELi0' ../_lib/var_$name/trace_f64.log | grep Used | head -1 | cut -c1-40)"
 done
