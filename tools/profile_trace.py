@@ -32,7 +32,8 @@ if args.reduce != "none":
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.launches + 1)]
 ev[0].record()
 for i in range(args.launches):
-    out = dev.trace_tensor(system.surfaces, materials, rays, keep=args.keep, wavelengths=[bench.WAVELENGTH],
+    keep = [int(v) for v in args.keep.split(',')] if args.keep[0].isdigit() or args.keep[0] == '-' else args.keep
+    out = dev.trace_tensor(system.surfaces, materials, rays, keep=keep, wavelengths=[bench.WAVELENGTH],
                            reducer=reducer, precision=args.precision, layout=args.layout)
     ev[i + 1].record()
 torch.cuda.synchronize()
