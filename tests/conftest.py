@@ -17,6 +17,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_library_built():
+    """The in-tree librtb.so is a build product (git-ignored): build it if a fresh checkout does not have it yet."""
+    import subprocess
+    lib = ROOT / "ray_trace_pb_b200" / "_lib" / "librtb.so"
+    if not lib.exists():
+        subprocess.run(["make", "-C", str(ROOT / "ray_trace_pb_b200" / "csrc"), "-j4"], check=True,
+                       stdout=subprocess.DEVNULL)
+
+
 @pytest.fixture(scope="session")
 def rt():
     import ray_trace_pb_b200.raytrace as rt
