@@ -36,6 +36,16 @@ def pack_surface(s) -> _ffi.RtbSurface:
         raise NotImplementedError(
             f"{type(s).__name__} has no device_record(): only FlatSurface, SphericalSurface, PlaneMirror and "
             f"PerfectLens (and subclasses that keep their geometry) can be traced; there is no CPU fallback")
+    # a subclass that re-defines the ray arithmetic cannot be honoured by the kernel: refuse rather than ignore it
+    from . import raytrace as _rt
+    known = next((k for k in type(s).__mro__ if k in (_rt.FlatSurface, _rt.SphericalSurface, _rt.PlaneMirror,
+                                                       _rt.PerfectLens)), None)
+    if known is not None and type(s) is not known:
+        for name in ("propagate", "get_intersect", "get_normal", "is_pt_on_surface"):
+            if getattr(type(s), name) is not getattr(known, name):
+                raise NotImplementedError(
+                    f"{type(s).__name__} overrides {name}(); the GPU trace only implements {known.__name__}'s own "
+                    f"geometry (no CPU fallback)")
     d = rec()
     out = _ffi.RtbSurface()
     out.kind = d["kind"]

@@ -98,6 +98,17 @@ def test_packing_rejects_unknown_objects(rt, rtm):
     w = Weird([0, 0, 1], [0, 0, 1], [0, 0, 0], [0, 0, 0], 1.0)
     with pytest.raises(NotImplementedError):
         engine.pack_system([w], [rtm.Vacuum(), rtm.Vacuum()])
+
+    class BentFlat(rt.FlatSurface):          # re-defines the geometry: must be refused, not silently ignored
+        def get_normal(self, pts):
+            return super().get_normal(pts) * 0.5
+
+    class TaggedFlat(rt.FlatSurface):        # adds bookkeeping only: fine
+        label = "stop"
+
+    with pytest.raises(NotImplementedError, match="overrides get_normal"):
+        engine.pack_system([BentFlat([0, 0, 0], [0, 0, 1], 1.0)], [rtm.Vacuum(), rtm.Vacuum()])
+    assert engine.pack_system([TaggedFlat([0, 0, 0], [0, 0, 1], 1.0)], [rtm.Vacuum(), rtm.Vacuum()]).n_surfaces == 1
     with pytest.raises(ValueError):
         engine.pack_system([], [rtm.Vacuum(), rtm.Vacuum()])
     # user media with their own n() need the host table
