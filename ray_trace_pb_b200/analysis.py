@@ -15,6 +15,36 @@ def _materials(system, initial_material, final_material):
     return [initial_material] + list(system.materials) + [final_material]
 
 
+class _Launcher:
+    """Packs the prescription once per wavelength and spreads independent launches over a few streams, so the tail
+    of one launch overlaps the head of the next (the launches of a sweep are small: a few million rays each)."""
+
+    def __init__(self, system, mats, device, n_streams=4):
+        import torch
+        self.torch = torch
+        self.system, self.mats, self.device = system, mats, device
+        self.packed = {}
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
+        self.turn = 0
+        self.origin_stream = torch.cuda.current_stream(device)
+
+    def launch(self, src, first, count, precision, red):
+        key = src.wavelength
+        if key not in self.packed:
+            self.packed[key] = dev.prepare(self.system.surfaces, self.mats,
+                                           [src.wavelength] if np.isfinite(src.wavelength) else None)
+        stream = self.streams[self.turn % len(self.streams)]
+        self.turn += 1
+        stream.wait_stream(self.origin_stream)
+        with self.torch.cuda.stream(stream):
+            dev.trace_source(self.system.surfaces, self.mats, src, first=first, count=count, keep="none",
+                             precision=precision, reducer=red, device=self.device, packed=self.packed[key])
+
+    def join(self):
+        for st in self.streams:
+            self.origin_stream.wait_stream(st)
+
+
 def spot_statistics(system, initial_material, final_material, sources, slab: int = -2, origin=None,
                     e1=(1.0, 0.0, 0.0), e2=(0.0, 1.0, 0.0), precision: str = "f64", device: int = 0,
                     chunk: int = 1 << 27):
@@ -31,14 +61,15 @@ def spot_statistics(system, initial_material, final_material, sources, slab: int
     if origin is None:
         origin = system.surfaces[max(slab - 1, 0) // 2].center
     mats = _materials(system, initial_material, final_material)
-    results = []
+    run = _Launcher(system, mats, device)
+    reducers = []
     for src in sources:
-        red = dev.Reducer(slab, origin=origin, e1=e1, e2=e2, device=device)
+        red = dev.Reducer(slab, origin=origin, e1=e1, e2=e2, device=device)     # reset on the caller's stream
+        reducers.append(red)
         for first in range(0, src.n_rays, chunk):
-            count = min(chunk, src.n_rays - first)
-            dev.trace_source(system.surfaces, mats, src, first=first, count=count, keep="none", precision=precision,
-                             reducer=red, device=device)
-        results.append(red.stats())
+            run.launch(src, first, min(chunk, src.n_rays - first), precision, red)
+    run.join()
+    results = [red.stats() for red in reducers]
     return results[0] if single else results
 
 
@@ -55,10 +86,10 @@ def pupil_grid(system, initial_material, final_material, source, slab: int, orig
     mats = _materials(system, initial_material, final_material)
     red = dev.Reducer(slab, origin=origin, e1=e1, e2=e2, grid_n=grid_n, half_width=half_width, phase_ref=phase_ref,
                       device=device)
+    run = _Launcher(system, mats, device, n_streams=2)
     for first in range(0, source.n_rays, chunk):
-        count = min(chunk, source.n_rays - first)
-        dev.trace_source(system.surfaces, mats, source, first=first, count=count, keep="none", precision=precision,
-                         reducer=red, device=device)
+        run.launch(source, first, min(chunk, source.n_rays - first), precision, red)
+    run.join()
     return red
 
 

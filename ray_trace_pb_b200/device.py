@@ -200,16 +200,26 @@ class RaySource:
         return out
 
 
+def prepare(surfaces, materials, wavelengths):
+    """
+    Pack a prescription once for many launches (sweeps over fields / chunks): returns an opaque object accepted as
+    ``packed=`` by :func:`trace_source`.  ``wavelengths``: the distinct wavelengths to tabulate (or None).
+    """
+    return _system_for(surfaces, materials, wavelengths)
+
+
 def trace_source(surfaces, materials, source: RaySource, first: int = 0, count: int | None = None, keep="last",
-                 precision="f64", reducer=None, device: int = 0, out=None):
+                 precision="f64", reducer=None, device: int = 0, out=None, packed=None):
     """
     Generate-and-trace in one kernel: rays [first, first+count) of ``source`` never exist in memory.
-    The refractive-index table is built from the source's single wavelength.
+    The refractive-index table is built from the source's single wavelength (or taken from ``packed``, see
+    :func:`prepare`, which must tabulate that wavelength).  Enqueued on the current stream of ``device``.
     """
     torch = _torch()
     _ffi.require_device()
     count = source.n_rays - first if count is None else count
-    packed = _system_for(surfaces, materials, [source.wavelength] if np.isfinite(source.wavelength) else None)
+    if packed is None:
+        packed = _system_for(surfaces, materials, [source.wavelength] if np.isfinite(source.wavelength) else None)
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
     opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
     if n_out == 0:
