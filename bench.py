@@ -364,7 +364,7 @@ def main():
         }
         if stats is not None:
             line["config"]["reduce_count"] = stats["count"]
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # the CPU baseline is reported at N = 1 only
             cores = os.cpu_count() or 1
             v, sample = cpu_baseline_run(cores)
             line["cpu_baseline"] = {"value": v, "unit": "ray*surfaces/s", "cores": cores, "kind": "port", "sample": sample}
