@@ -103,6 +103,12 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
         // Live rays run the surface loop; a ray that dies (leaves a surface all-NaN) drops out of it and only has
         // its remaining slabs blanked below -- an all-NaN ray stays all-NaN through every kind of surface.
         bool dead = false;
+        // The optimistic steps may assume finite geometry (that is what licenses their shortcuts), and inside a trace
+        // it always is -- the reference blanks x, y, z together.  Only a ray that ARRIVES with an inf/NaN in some
+        // position or direction column could break that, so such a ray takes the careful path at its first surface.
+        auto non_finite = [](double v) { return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000; };
+        bool force_careful = non_finite(cur.ox) | non_finite(cur.oy) | non_finite(cur.oz) | non_finite(cur.dx) |
+                             non_finite(cur.dy) | non_finite(cur.dz);
         int k = 0;
 #ifdef RTB_SURFACE_UNROLL2
 #pragma unroll 2
@@ -128,6 +134,8 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             // run the surface optimistically; one flag says whether every intermediate stayed in the fast
             // paths' domain, otherwise redo this surface with the Careful arithmetic (surface_steps.cuh)
             Optimistic m;
+            m.ok = !force_careful;
+            force_careful = false;
             AtRaw raw;
             Ray after;
             if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {

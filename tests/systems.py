@@ -380,6 +380,26 @@ def edge_mix(rt, rtm, n=600, seed=11):
     return system, rtm.Vacuum(), rtm.Vacuum(), rays
 
 
+def invalid_inputs(rt, rtm, n=1200, seed=21):
+    """launch rays with inf / NaN in single columns, through the edge-mix system (users can pass these; the reference
+    itself only ever blanks x, y, z together)"""
+    system, m_in, m_out, _ = edge_mix(rt, rtm)
+    rng = np.random.default_rng(seed)
+    rays = np.zeros((n, 8))
+    rays[:, 0:2] = rng.uniform(-4, 4, (n, 2))
+    rays[:, 2] = rng.uniform(-6, 0, n)
+    d = rng.standard_normal((n, 3)) * np.array([0.2, 0.2, 0.1]) + np.array([0, 0, 1.0])
+    rays[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 6] = rng.uniform(0, 100, n)
+    rays[:, 7] = rng.choice(np.array([0.405, 0.532, 0.785, 1.064]), size=n)
+    for col in range(8):
+        rows = rng.integers(0, n, 45)
+        rays[rows[:25], col] = np.nan
+        rays[rows[25:35], col] = np.inf
+        rays[rows[35:], col] = -np.inf
+    return system, m_in, m_out, rays
+
+
 def reversed_doublet(rt, rtm, n_disps=21, nphis=4):
     """System.reverse() flips input_axis only (raytrace.py:402-415): trace right-to-left through a doublet"""
     doublet = rt.Doublet(rtm.Nbak4(), rtm.Sf10(), radius_crown=61.5, radius_flint=-128.2, radius_interface=-44.6,
@@ -404,6 +424,7 @@ CASES = {
     "cauchy_singlet": cauchy_singlet,
     "edge_mix": edge_mix,
     "reversed_doublet": reversed_doublet,
+    "invalid_inputs": invalid_inputs,
 }
 
 # cases whose refractive indices go through np.power (Ebaf11) and are therefore only bit-reproducible on a host

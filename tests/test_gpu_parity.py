@@ -100,6 +100,23 @@ def test_fuzz_edge_mix_vs_oracle(rt, rtm, oracle):
     assert 0.05 < dead < 0.98
 
 
+def test_partially_invalid_input_rays_vs_oracle(rt, rtm, oracle):
+    """inf / NaN in single columns of the launch rays (the reference never produces these itself, users can)"""
+    rng = np.random.default_rng(21)
+    for builder in (systems.edge_mix, systems.plano_convex, systems.mirrors, systems.perfect_lens_phase):
+        system, m_in, m_out, _ = builder(rt, rtm)
+        rays = _fuzz_rays(4000, seed=5, zlo=-6.0, spread=0.2)
+        rays[:, 0:2] *= 0.3
+        for col in range(8):
+            rows = rng.integers(0, rays.shape[0], 60)
+            rays[rows[:30], col] = np.nan
+            rays[rows[30:45], col] = np.inf
+            rays[rows[45:], col] = -np.inf
+        got = system.ray_trace(rays, m_in, m_out)
+        want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+        parity.assert_bit_identical(got, want, builder.__name__)
+
+
 def test_fuzz_opm_vs_oracle(rt, rtm, oracle):
     system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
     rays = rt.get_ray_fan([1e-3, -2e-3, 5e-4], 1.05 * alpha1, 301, 532e-6, nphis=97)
