@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
         const DevSurface &s = P.surf[k];
         const double den = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
         s_c.rcp_radius[k] = xm::refine_rcp(den);
-        if (xm::den_ok(den)) atomicOr(&s_c.rcp_ok, 1ull << k);
+        // usable by the Optimistic steps: finite, |den| < 2^52, and a reciprocal that is an ordinary normal number
+        const bool sane = xm::den_ok(den) && fabs(den) < 4503599627370496.0 && xm::quo_ok(s_c.rcp_radius[k]);
+        if (sane) atomicOr(&s_c.rcp_ok, 1ull << k);
     }
     __syncthreads();
 
