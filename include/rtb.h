@@ -118,7 +118,9 @@ typedef struct rtb_system {
 
 typedef enum rtb_precision {
     RTB_F64_EXACT = 0, /* reference operation order, no FMA contraction: bit-identical to the NumPy path */
-    RTB_F32_FAST = 1   /* fp32 geometry, fp64 phase accumulation; tolerance stated in DESIGN.md          */
+    RTB_F32_FAST = 1,  /* fp32 geometry, fp64 positions / phase; tolerance stated in DESIGN.md section 8 */
+    RTB_F64_FAST = 2   /* all fp64 with FMA and the direct Snell form: ~1e-13 from the reference, but the
+                          round-off-dependent validity of knife-edge rays is not reproduced              */
 } rtb_precision;
 
 typedef enum rtb_keep_mode {

@@ -31,7 +31,7 @@ RTB_ERR_NOMEM = -4
 
 SURF_FLAT, SURF_SPHERE, SURF_MIRROR, SURF_PERFECT_LENS = 0, 1, 2, 3
 MAT_CONSTANT, MAT_SELLMEIER, MAT_TABLE_ONLY = 0, 1, 2
-F64_EXACT, F32_FAST = 0, 1
+F64_EXACT, F32_FAST, F64_FAST = 0, 1, 2
 KEEP_ALL, KEEP_LAST, KEEP_LIST, KEEP_NONE = 0, 1, 2, 3
 SRC_COLLIMATED, SRC_FAN, SRC_GRID = 0, 1, 2
 FLAG_INTERSECT_ONLY = 1

@@ -15,7 +15,7 @@
 
 namespace rtb {
 cudaError_t launch_trace_f64(const TraceParams &P, int sm_count, cudaStream_t stream);
-cudaError_t launch_trace_f32(const TraceParams &P, int sm_count, cudaStream_t stream);
+cudaError_t launch_trace_fast(const TraceParams &P, int precision, int sm_count, cudaStream_t stream);
 cudaError_t launch_generate(const DevSource &src, long long n_rays, double *out, int sm_count, cudaStream_t stream);
 cudaError_t launch_reduce_init(const DevReduce &red, int sm_count, cudaStream_t stream);
 cudaError_t launch_intersect(const double *r1, long long n1, const double *r2, long long n2, double *out,
@@ -273,7 +273,7 @@ int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TracePar
     default:
         return fail(RTB_ERR_INVALID, "unknown keep_mode %d", opts->keep_mode);
     }
-    if (opts->precision != RTB_F64_EXACT && opts->precision != RTB_F32_FAST)
+    if (opts->precision != RTB_F64_EXACT && opts->precision != RTB_F32_FAST && opts->precision != RTB_F64_FAST)
         return fail(RTB_ERR_INVALID, "unknown precision %d", opts->precision);
 
     P.flags = opts->flags;
@@ -345,8 +345,8 @@ int pack_source(const rtb_source *src, long long first, long long count, rtb::De
 
 int launch(const rtb::TraceParams &P, int precision, int sm_count, cudaStream_t stream)
 {
-    cudaError_t e = (precision == RTB_F32_FAST) ? rtb::launch_trace_f32(P, sm_count, stream)
-                                                : rtb::launch_trace_f64(P, sm_count, stream);
+    cudaError_t e = (precision == RTB_F64_EXACT) ? rtb::launch_trace_f64(P, sm_count, stream)
+                                                 : rtb::launch_trace_fast(P, precision, sm_count, stream);
     if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString(e));
     if (P.n_rays > 0) g_launches.fetch_add(1, std::memory_order_relaxed);
     return RTB_OK;

@@ -1,4 +1,4 @@
-// trace_f32.cu -- the fp32 geometry mode (RTB_F32_FAST).
+// trace_fast.cu -- the two fast modes: fp32 geometry (RTB_F32_FAST) and FMA fp64 (RTB_F64_FAST).
 //
 // Same sequential trace, same slab / NaN conventions and the same I/O (float64 (N, 8) rows) as the exact mode, but
 // built for speed instead of bit parity with NumPy:
@@ -12,7 +12,15 @@
 //   * a point produced by the intersection is on the surface by construction, so the reference's absolute 1e-12
 //     on-surface test (meaningless in fp32) reduces to "the intersection exists"; the aperture test is kept.
 //
-// Stated tolerance against the fp64 mode (asserted in tests/test_gpu_parity.py::test_f32_mode_tolerance):
+// The same code instantiated with T = double is the RTB_F64_FAST mode: all arithmetic fp64 with FMA and the direct
+// Snell form, ~3x fewer FP64 instructions than the exact mode.  It agrees with the reference to ~1e-13 (tolerance
+// below) but NOT in the validity masks of knife-edge rays: the reference's absolute 1e-12 on-surface test culls a few
+// rays in 1e5 purely on round-off, which only the exact mode reproduces.
+//
+// Stated tolerances against the exact mode (asserted in tests/test_gpu_parity.py::test_fast_modes_tolerance):
+//   RTB_F64_FAST: positions 1e-11 * L, directions 1e-12, phase 1e-12 relative (100x looser for high-NA perfect-lens
+//                 systems); NaN masks equal except knife-edge rays.
+//   RTB_F32_FAST:
 //   positions  |dp| <= 2e-6 * L   (L = 1000 mm, the length scale of the traced systems: 2 nm per mm of path)
 //   directions |dd| <= 2e-6
 //   phase      |dphi| <= 2e-6 * |phi|  (i.e. optical path length to 2e-6 relative)
@@ -31,28 +39,42 @@ namespace rtb {
 
 namespace {
 
-struct RayM {
+// T = float: fp32 directions / normals; T = double: everything fp64
+template <typename T>
+struct RayT {
     double ox, oy, oz; // position (fp64)
-    float dx, dy, dz;  // direction (fp32)
+    T dx, dy, dz;      // direction
     double ph;         // phase (fp64)
     double wl;
 };
 
-__device__ __forceinline__ float dot3f(float ax, float ay, float az, float bx, float by, float bz)
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_t(double x) { return xm::sqrt(x); }
+__device__ __forceinline__ float div_t(float a, float b) { return a / b; }
+__device__ __forceinline__ double div_t(double a, double b) { return xm::div(a, b); }
+__device__ __forceinline__ float abs_t(float x) { return fabsf(x); }
+__device__ __forceinline__ double abs_t(double x) { return fabs(x); }
+
+template <typename T>
+__device__ __forceinline__ T dot3f(T ax, T ay, T az, T bx, T by, T bz)
 {
-    return fmaf(az, bz, fmaf(ay, by, ax * bx));
+    return fma_t(az, bz, fma_t(ay, by, ax * bx));
 }
 
-__device__ __forceinline__ void set_nan(RayM &r)
+template <typename T>
+__device__ __forceinline__ void set_nan(RayT<T> &r)
 {
     const double q = CUDART_NAN;
     r.ox = q; r.oy = q; r.oz = q;
-    r.dx = CUDART_NAN_F; r.dy = CUDART_NAN_F; r.dz = CUDART_NAN_F;
+    r.dx = (T)q; r.dy = (T)q; r.dz = (T)q;
     r.ph = q;
     r.wl = q;
 }
 
-__device__ __forceinline__ Ray widen(const RayM &r)
+template <typename T>
+__device__ __forceinline__ Ray widen(const RayT<T> &r)
 {
     Ray o;
     o.ox = r.ox; o.oy = r.oy; o.oz = r.oz;
@@ -62,40 +84,31 @@ __device__ __forceinline__ Ray widen(const RayM &r)
     return o;
 }
 
-__device__ __forceinline__ RayM narrow(const Ray &r)
-{
-    RayM o;
-    o.ox = r.ox; o.oy = r.oy; o.oz = r.oz;
-    o.dx = (float)r.dx; o.dy = (float)r.dy; o.dz = (float)r.dz;
-    o.ph = r.ph;
-    o.wl = r.wl;
-    return o;
-}
-
-// per-surface constants in fp32
+// per-surface constants in the working precision
+template <typename T>
 struct SurfF {
-    float nx, ny, nz, ax, ay, az;
-    float inv_radius, aperture_sq, focal_len, sin_alpha;
+    T nx, ny, nz, ax, ay, az;
+    T focal_len, sin_alpha;
 };
 
-__device__ __forceinline__ SurfF surf_f32(const DevSurface &s, float inv_radius)
+template <typename T>
+__device__ __forceinline__ SurfF<T> surf_consts(const DevSurface &s)
 {
-    SurfF f;
-    f.nx = (float)s.nx; f.ny = (float)s.ny; f.nz = (float)s.nz;
-    f.ax = (float)s.ax; f.ay = (float)s.ay; f.az = (float)s.az;
-    f.inv_radius = inv_radius; // 1/R, computed once per block
-    f.aperture_sq = (float)(s.aperture * s.aperture);
-    f.focal_len = (float)s.focal_len;
-    f.sin_alpha = (float)s.sin_alpha;
+    SurfF<T> f;
+    f.nx = (T)s.nx; f.ny = (T)s.ny; f.nz = (T)s.nz;
+    f.ax = (T)s.ax; f.ay = (T)s.ay; f.az = (T)s.az;
+    f.focal_len = (T)s.focal_len;
+    f.sin_alpha = (T)s.sin_alpha;
     return f;
 }
 
 // ray -> plane through (cx, cy, cz) with normal n; t in fp32, position and phase in fp64.  Returns t.
-__device__ __forceinline__ float to_plane_f(const RayM &in, float nx, float ny, float nz, double cx, double cy, double cz,
-                                            double k_n, double &px, double &py, double &pz, double &ph)
+template <typename T>
+__device__ __forceinline__ T to_plane_f(const RayT<T> &in, T nx, T ny, T nz, double cx, double cy, double cz, double k_n,
+                                        double &px, double &py, double &pz, double &ph)
 {
-    const float rx = (float)(in.ox - cx), ry = (float)(in.oy - cy), rz = (float)(in.oz - cz);
-    const float t = -dot3f(rx, ry, rz, nx, ny, nz) / dot3f(in.dx, in.dy, in.dz, nx, ny, nz);
+    const T rx = (T)(in.ox - cx), ry = (T)(in.oy - cy), rz = (T)(in.oz - cz);
+    const T t = div_t(-dot3f(rx, ry, rz, nx, ny, nz), dot3f(in.dx, in.dy, in.dz, nx, ny, nz));
     const double td = (double)t;
     px = fma((double)in.dx, td, in.ox);
     py = fma((double)in.dy, td, in.oy);
@@ -105,88 +118,64 @@ __device__ __forceinline__ float to_plane_f(const RayM &in, float nx, float ny, 
 }
 
 // refraction / reflection of unit d at unit normal n; mu = n1/n2 (mu < 0 selects reflection)
-__device__ __forceinline__ void bend(float dx, float dy, float dz, float nx, float ny, float nz, float mu, bool reflect,
-                                     float &ex, float &ey, float &ez)
+template <typename T>
+__device__ __forceinline__ void bend(T dx, T dy, T dz, T nx, T ny, T nz, T mu, bool reflect, T &ex, T &ey, T &ez)
 {
-    const float c = dot3f(nx, ny, nz, dx, dy, dz);
+    const T c = dot3f(nx, ny, nz, dx, dy, dz);
     if (reflect) {
-        ex = fmaf(-2.0f * c, nx, dx);
-        ey = fmaf(-2.0f * c, ny, dy);
-        ez = fmaf(-2.0f * c, nz, dz);
+        ex = fma_t((T)-2 * c, nx, dx);
+        ey = fma_t((T)-2 * c, ny, dy);
+        ez = fma_t((T)-2 * c, nz, dz);
         return;
     }
-    const float tx = fmaf(-c, nx, dx), ty = fmaf(-c, ny, dy), tz = fmaf(-c, nz, dz);
-    const float s2 = mu * mu * dot3f(tx, ty, tz, tx, ty, tz);
-    const float root = sqrtf(1.0f - s2);                       // NaN beyond the critical angle
-    const float w = (c > 0.0f) ? root : ((c < 0.0f) ? -root : 0.0f * root);
-    ex = fmaf(mu, tx, w * nx);
-    ey = fmaf(mu, ty, w * ny);
-    ez = fmaf(mu, tz, w * nz);
-}
-
-__device__ __forceinline__ void finish(bool on, double px, double py, double pz, float ex, float ey, float ez, double ph,
-                                       double wl, RayM &after)
-{
-    if (!on) {
-        set_nan(after);
-        return;
-    }
-    const bool dead_dir = ex != ex;
-    const double q = CUDART_NAN;
-    after.ox = dead_dir ? q : px;
-    after.oy = dead_dir ? q : py;
-    after.oz = dead_dir ? q : pz;
-    after.dx = ex; after.dy = ey; after.dz = ez;
-    after.ph = ph;
-    after.wl = wl;
-}
-
-__device__ __forceinline__ void fill_at_f(bool kill, double px, double py, double pz, double ph, const RayM &in, RayM &at)
-{
-    at = in;
-    at.ox = px; at.oy = py; at.oz = pz;
-    at.ph = ph;
-    if (kill) set_nan(at);
+    const T tx = fma_t(-c, nx, dx), ty = fma_t(-c, ny, dy), tz = fma_t(-c, nz, dz);
+    const T s2 = mu * mu * dot3f(tx, ty, tz, tx, ty, tz);
+    const T root = sqrt_t((T)1 - s2);                          // NaN beyond the critical angle
+    const T w = (c > (T)0) ? root : ((c < (T)0) ? -root : (T)0 * root);
+    ex = fma_t(mu, tx, w * nx);
+    ey = fma_t(mu, ty, w * ny);
+    ez = fma_t(mu, tz, w * nz);
 }
 
 // PerfectLens.propagate (raytrace.py:1601-1801)
-__device__ __forceinline__ bool lens_step(const DevSurface &s, const RayM &in, double k, double n1, double n2,
-                                          bool as_get_intersect, RayM &before, RayM &after)
+template <typename T>
+__device__ __forceinline__ bool lens_step(const DevSurface &s, const RayT<T> &in, double k, double n1, double n2,
+                                          bool as_get_intersect, RayT<T> &before, RayT<T> &after)
 {
-    const SurfF f = surf_f32(s, 0.0f);
+    const SurfF<T> f = surf_consts<T>(s);
     const double fx = fma(-s.nfx, n1, s.cx), fy = fma(-s.nfy, n1, s.cy), fz = fma(-s.nfz, n1, s.cz);
     const double gx = fma(s.nfx, n2, s.cx), gy = fma(s.nfy, n2, s.cy), gz = fma(s.nfz, n2, s.cz);
     double ax, ay, az, ph_ffp;
     to_plane_f(in, f.nx, f.ny, f.nz, fx, fy, fz, k * n1, ax, ay, az, ph_ffp);
 
-    const float rnd = dot3f(in.dx, in.dy, in.dz, f.nx, f.ny, f.nz);
-    float px = fmaf(-rnd, f.nx, in.dx), py = fmaf(-rnd, f.ny, in.dy), pz = fmaf(-rnd, f.nz, in.dz);
-    const float pn = sqrtf(dot3f(px, py, pz, px, py, pz));
-    if (pn > 1e-12f) {
-        const float inv = 1.0f / pn;
+    const T rnd = dot3f(in.dx, in.dy, in.dz, f.nx, f.ny, f.nz);
+    T px = fma_t(-rnd, f.nx, in.dx), py = fma_t(-rnd, f.ny, in.dy), pz = fma_t(-rnd, f.nz, in.dz);
+    const T pn = sqrt_t(dot3f(px, py, pz, px, py, pz));
+    if (pn > (T)1e-12) {
+        const T inv = div_t((T)1, pn);
         px *= inv; py *= inv; pz *= inv;
     }
-    const float hx = (float)(ax - fx), hy = (float)(ay - fy), hz = (float)(az - fz);
-    const float hn = sqrtf(dot3f(hx, hy, hz, hx, hy, hz));
-    float ux = hx, uy = hy, uz = hz;
-    if (hn != 0.0f) {
-        const float inv = 1.0f / hn;
+    const T hx = (T)(ax - fx), hy = (T)(ay - fy), hz = (T)(az - fz);
+    const T hn = sqrt_t(dot3f(hx, hy, hz, hx, hy, hz));
+    T ux = hx, uy = hy, uz = hz;
+    if (hn != (T)0) {
+        const T inv = div_t((T)1, hn);
         ux *= inv; uy *= inv; uz *= inv;
     }
-    const float sin_t1 = dot3f(px, py, pz, in.dx, in.dy, in.dz);
+    const T sin_t1 = dot3f(px, py, pz, in.dx, in.dy, in.dz);
 
-    RayM rb;
+    RayT<T> rb;
     const double scale = n1 * s.focal_len * (double)sin_t1;
     rb.ox = fma(scale, (double)px, gx);
     rb.oy = fma(scale, (double)py, gy);
     rb.oz = fma(scale, (double)pz, gz);
-    const float sin_t2 = -hn / f.focal_len / (float)n2;
-    const float cos_t2 = sqrtf(1.0f - sin_t2 * sin_t2);
-    rb.dx = fmaf(sin_t2, ux, cos_t2 * f.nx);
-    rb.dy = fmaf(sin_t2, uy, cos_t2 * f.ny);
-    rb.dz = fmaf(sin_t2, uz, cos_t2 * f.nz);
+    const T sin_t2 = div_t(div_t(-hn, f.focal_len), (T)n2);
+    const T cos_t2 = sqrt_t((T)1 - sin_t2 * sin_t2);
+    rb.dx = fma_t(sin_t2, ux, cos_t2 * f.nx);
+    rb.dy = fma_t(sin_t2, uy, cos_t2 * f.ny);
+    rb.dz = fma_t(sin_t2, uz, cos_t2 * f.nz);
     rb.wl = in.wl;
-    const bool culled = (fabsf(sin_t1) > f.sin_alpha) || (fabsf(sin_t2) > f.sin_alpha);
+    const bool culled = (abs_t(sin_t1) > f.sin_alpha) || (abs_t(sin_t2) > f.sin_alpha);
     if (culled) set_nan(rb);
     const double plane_wave = (double)dot3f(hx, hy, hz, in.dx, in.dy, in.dz);
     rb.ph = (ph_ffp - (k * n1) * plane_wave) + k * ((n1 * n1) * s.focal_len + (n2 * n2) * s.focal_len);
@@ -195,36 +184,36 @@ __device__ __forceinline__ bool lens_step(const DevSurface &s, const RayM &in, d
     after.dx = rb.dx; after.dy = rb.dy; after.dz = rb.dz;
     after.wl = rb.wl;
     before = in;
-    const float tb = to_plane_f(in, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n1, before.ox, before.oy, before.oz,
+    const T tb = to_plane_f(in, f.nx, f.ny, f.nz, s.cx, s.cy, s.cz, k * n1, before.ox, before.oy, before.oz,
                                 before.ph);
-    if (as_get_intersect && tb < 0.0f) set_nan(before);
+    if (as_get_intersect && tb < (T)0) set_nan(before);
     return culled;
 }
 
-template <bool USE_TABLE, bool FROM_SOURCE>
-__global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant__ TraceParams P)
+template <typename T, bool USE_TABLE, bool FROM_SOURCE>
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel(const __grid_constant__ TraceParams P)
 {
     __shared__ double s_ntab[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     __shared__ double s_ratio[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     // per-surface fp32 constants and the fp32 copy of n1/n2, converted once per block (conversions run on the
     // quarter-rate XU pipe, so they must not be repeated per ray)
-    __shared__ float s_geo[kMaxSurfaces][8];   // normal xyz, axis xyz, 1/R, aperture^2 (unused slot)
-    __shared__ float s_ratio_f[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
+    __shared__ T s_geo[kMaxSurfaces][8];   // normal xyz, axis xyz, 1/R, aperture^2 (unused slot)
+    __shared__ T s_ratio_f[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     const int n_med = P.n_surf + 1;
     if (USE_TABLE) {
         const int count = (P.n_wl + 1) * n_med;
         for (int k = threadIdx.x; k < count; k += blockDim.x) {
             s_ntab[k] = P.n_tab[k];
             s_ratio[k] = P.ratio_tab[k];
-            s_ratio_f[k] = (float)P.ratio_tab[k];
+            s_ratio_f[k] = (T)P.ratio_tab[k];
         }
     }
     for (int k = threadIdx.x; k < P.n_surf; k += blockDim.x) {
         const DevSurface &s = P.surf[k];
-        s_geo[k][0] = (float)s.nx; s_geo[k][1] = (float)s.ny; s_geo[k][2] = (float)s.nz;
-        s_geo[k][3] = (float)s.ax; s_geo[k][4] = (float)s.ay; s_geo[k][5] = (float)s.az;
-        s_geo[k][6] = (float)(1.0 / s.radius);
-        s_geo[k][7] = 0.0f;
+        s_geo[k][0] = (T)s.nx; s_geo[k][1] = (T)s.ny; s_geo[k][2] = (T)s.nz;
+        s_geo[k][3] = (T)s.ax; s_geo[k][4] = (T)s.ay; s_geo[k][5] = (T)s.az;
+        s_geo[k][6] = (T)(1.0 / s.radius);
+        s_geo[k][7] = (T)0;
     }
     __syncthreads();
     const bool reducing = P.red.slab >= 0;
@@ -247,7 +236,7 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
         // the ray, in registers: position / phase fp64, direction fp32; the wavelength only ever turns NaN with the
         // whole ray (dead)
         double ox = first.ox, oy = first.oy, oz = first.oz, ph = first.ph;
-        float dx = (float)first.dx, dy = (float)first.dy, dz = (float)first.dz;
+        T dx = (T)first.dx, dy = (T)first.dy, dz = (T)first.dz;
         const double wl0 = first.wl;
         const double k = kTwoPi / wl0;
         int row = 0;
@@ -282,7 +271,7 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                     if (act & 10) emit(false, w);
                 }
             } else if (s.kind == RTB_SURF_PERFECT_LENS) {
-                RayM cur, at, after;
+                RayT<T> cur, at, after;
                 cur.ox = ox; cur.oy = oy; cur.oz = oz; cur.dx = dx; cur.dy = dy; cur.dz = dz; cur.ph = ph;
                 cur.wl = wl0;
                 dead = lens_step(s, cur, k, n1, n2, intersect_only, at, after);
@@ -293,16 +282,16 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                 // ---- flat / sphere refraction and plane mirror (raytrace.py:1160-1303) ----
                 const bool mirror = s.kind == RTB_SURF_MIRROR;
                 const double ddx = (double)dx, ddy = (double)dy, ddz = (double)dz;
-                const float snx = s_geo[q][0], sny = s_geo[q][1], snz = s_geo[q][2];
+                const T snx = s_geo[q][0], sny = s_geo[q][1], snz = s_geo[q][2];
                 double px, py, pz, ph_at;
-                float nx, ny, nz;
+                T nx, ny, nz;
                 bool kill = false, on;
                 if (s.kind == RTB_SURF_SPHERE) {
                     // quadratic in fp64 (raytrace.py:1497-1509), root in fp32
                     const double qx = ox - s.cx, qy = oy - s.cy, qz = oz - s.cz;
                     const double b = fma(ddz, qz, fma(ddy, qy, ddx * qx));
                     const double cq = fma(qz, qz, fma(qy, qy, qx * qx)) - s.radius_sq;
-                    const double root = (double)sqrtf((float)fma(b, b, -cq));
+                    const double root = (double)sqrt_t((T)fma(b, b, -cq));
                     const double t1 = root - b, t2 = -b - root;
                     double t = (t2 < 0.0) ? t1 : t2;
                     t = (t1 < 0.0 || root != root) ? CUDART_NAN : t;
@@ -310,30 +299,30 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                     py = fma(ddy, t, oy);
                     pz = fma(ddz, t, oz);
                     ph_at = fma(t, k * n1, ph);
-                    const float inv_r = s_geo[q][6];
-                    nx = (float)(px - s.cx) * inv_r;
-                    ny = (float)(py - s.cy) * inv_r;
-                    nz = (float)(pz - s.cz) * inv_r;
+                    const T inv_r = s_geo[q][6];
+                    nx = (T)(px - s.cx) * inv_r;
+                    ny = (T)(py - s.cy) * inv_r;
+                    nz = (T)(pz - s.cz) * inv_r;
                     // aperture measured from the axis through the origin (raytrace.py:1530-1533); fp64 is cheaper
                     // here than three more conversions
                     const double along = fma(pz, s.az, fma(py, s.ay, px * s.ax));
                     const double ux = fma(-along, s.ax, px), uy = fma(-along, s.ay, py), uz = fma(-along, s.az, pz);
                     on = fma(uz, uz, fma(uy, uy, ux * ux)) <= s.aperture * s.aperture;
                 } else {
-                    const float rx = (float)(ox - s.cx), ry = (float)(oy - s.cy), rz = (float)(oz - s.cz);
-                    const float t = -dot3f(rx, ry, rz, snx, sny, snz) / dot3f(dx, dy, dz, snx, sny, snz);
+                    const T rx = (T)(ox - s.cx), ry = (T)(oy - s.cy), rz = (T)(oz - s.cz);
+                    const T t = div_t(-dot3f(rx, ry, rz, snx, sny, snz), dot3f(dx, dy, dz, snx, sny, snz));
                     const double td = (double)t;
                     px = fma(ddx, td, ox);
                     py = fma(ddy, td, oy);
                     pz = fma(ddz, td, oz);
                     ph_at = fma(td, k * n1, ph);
-                    kill = t < 0.0f;
+                    kill = t < (T)0;
                     nx = snx; ny = sny; nz = snz;
                     const double ux = px - s.cx, uy = py - s.cy, uz = pz - s.cz;
                     on = fma(uz, uz, fma(uy, uy, ux * ux)) <= s.aperture * s.aperture;
                 }
                 if (!intersect_only && !mirror)
-                    kill = kill || (dot3f(dx, dy, dz, s_geo[q][3], s_geo[q][4], s_geo[q][5]) < 0.0f);
+                    kill = kill || (dot3f(dx, dy, dz, s_geo[q][3], s_geo[q][4], s_geo[q][5]) < (T)0);
                 on = on && !kill;
                 if (act & 5) {
                     Ray w;
@@ -342,8 +331,8 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
                     if (kill) set_nan(w);
                     emit(true, w);
                 }
-                const float ratio = (USE_TABLE && !unlisted) ? s_ratio_f[row + q] : (float)(n1 / n2);
-                float ex, ey, ez;
+                const T ratio = (USE_TABLE && !unlisted) ? s_ratio_f[row + q] : (T)(n1 / n2);
+                T ex, ey, ez;
                 bend(dx, dy, dz, nx, ny, nz, ratio, mirror, ex, ey, ez);
                 dead = !on;
                 const bool no_dir = ex != ex;             // beyond the critical angle: position blanked too
@@ -366,27 +355,33 @@ __global__ void __launch_bounds__(128, 6) trace_f32_kernel(const __grid_constant
     if (reducing) tally_flush(P.red, tally);
 }
 
+template <typename T>
+cudaError_t launch_fast(const TraceParams &P, unsigned b, int threads, cudaStream_t stream)
+{
+    const bool table = P.n_wl > 0;
+    const bool source = P.src.kind >= 0;
+    if (table && source)
+        trace_fast_kernel<T, true, true><<<b, threads, 0, stream>>>(P);
+    else if (table)
+        trace_fast_kernel<T, true, false><<<b, threads, 0, stream>>>(P);
+    else if (source)
+        trace_fast_kernel<T, false, true><<<b, threads, 0, stream>>>(P);
+    else
+        trace_fast_kernel<T, false, false><<<b, threads, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 } // namespace
 
-cudaError_t launch_trace_f32(const TraceParams &P, int sm_count, cudaStream_t stream)
+cudaError_t launch_trace_fast(const TraceParams &P, int precision, int sm_count, cudaStream_t stream)
 {
     if (P.n_rays <= 0) return cudaSuccess;
     const int threads = 128;
     long long blocks = (P.n_rays + threads - 1) / threads;
     const long long max_blocks = (long long)sm_count * 32;
     if (blocks > max_blocks) blocks = max_blocks;
-    const bool table = P.n_wl > 0;
-    const bool source = P.src.kind >= 0;
-    const unsigned b = (unsigned)blocks;
-    if (table && source)
-        trace_f32_kernel<true, true><<<b, threads, 0, stream>>>(P);
-    else if (table)
-        trace_f32_kernel<true, false><<<b, threads, 0, stream>>>(P);
-    else if (source)
-        trace_f32_kernel<false, true><<<b, threads, 0, stream>>>(P);
-    else
-        trace_f32_kernel<false, false><<<b, threads, 0, stream>>>(P);
-    return cudaGetLastError();
+    return precision == RTB_F64_FAST ? launch_fast<double>(P, (unsigned)blocks, threads, stream)
+                                     : launch_fast<float>(P, (unsigned)blocks, threads, stream);
 }
 
 } // namespace rtb

@@ -188,7 +188,10 @@ def resolve_keep(keep, n_slabs: int):
 
 def make_opts(keep_mode, keep_idx, precision="f64", reduce=None):
     opts = _ffi.RtbTraceOpts()
-    opts.precision = {"f64": _ffi.F64_EXACT, "f32": _ffi.F32_FAST}[precision]
+    try:
+        opts.precision = {"f64": _ffi.F64_EXACT, "f32": _ffi.F32_FAST, "f64_fast": _ffi.F64_FAST}[precision]
+    except KeyError:
+        raise ValueError(f"precision must be 'f64', 'f64_fast' or 'f32', got {precision!r}") from None
     opts.keep_mode = keep_mode
     if keep_idx is not None:
         opts.n_keep = len(keep_idx)

@@ -17,7 +17,7 @@ What runs where
   the prescriptions it builds are the ones the reference would build.
 
 Extensions over the reference signature (all keyword-only, defaults reproduce the reference):
-``System.ray_trace(..., keep="all" | "last" | [slab indices], precision="f64" | "f32", device=0)``.
+``System.ray_trace(..., keep="all" | "last" | [slab indices], precision="f64" | "f64_fast" | "f32", device=0)``.
 """
 from __future__ import annotations
 

@@ -577,17 +577,21 @@ def test_auto_focus_ray_modes(rt, rtm, host_api):
         np.testing.assert_allclose(got[~np.isnan(got)], want[~np.isnan(want)], rtol=1e-9)
 
 
+@pytest.mark.parametrize("precision", ["f32", "f64_fast"])
 @pytest.mark.parametrize("name", ["relay10_script", "doublet_nlak22", "opm", "mirrors", "edge_mix", "plano_convex_3d"])
-def test_f32_mode_tolerance(name, rt, rtm):
+def test_fast_modes_tolerance(name, precision, rt, rtm):
     """
-    fp32 geometry mode against the fp64 reference history, at the tolerance stated in csrc/trace_f32.cu:
-    positions 2e-6 * L (L = 1000 mm), directions 2e-6, phase 2e-6 relative; NaN masks equal except for rays that sit
-    within tolerance of an aperture edge / grazing intersection / critical angle (at most a few per mille).
+    The two fast modes against the reference history, at the tolerances stated in csrc/trace_fast.cu:
+      f32       positions 2e-6 * L (L = 1000 mm), directions 2e-6, phase 2e-6 relative
+      f64_fast  positions 1e-11 * L, directions 1e-12, phase 1e-12 relative
+    (10x / 100x looser for the high-NA perfect-lens system and the deliberately extreme edge-mix rays, where the
+    direction error is amplified by 1/cos(theta)); NaN masks equal except for rays that sit within tolerance of an
+    aperture edge / grazing intersection / critical angle, or that the reference culls on round-off alone.
     """
     g = load_golden(name)
     system, m_in, m_out = systems.rebuild_system(g["system"], rt, rtm)
     want = g["history"]
-    got = system.ray_trace(g["rays_in"], m_in, m_out, precision="f32")
+    got = system.ray_trace(g["rays_in"], m_in, m_out, precision=precision)
     assert got.shape == want.shape
     flips = np.isnan(got) != np.isnan(want)
     ray_flips = flips.any(axis=(0, 2)).mean()
@@ -596,14 +600,15 @@ def test_f32_mode_tolerance(name, rt, rtm):
     with np.errstate(invalid="ignore"):
         err = np.abs(got - want)
     scale = np.abs(want)
-    pos_ok = ok[..., 0:3]
-    # high-NA perfect lenses (sin(theta) up to 0.96) and the deliberately extreme edge-mix rays amplify the fp32
-    # direction error by 1/cos(theta): 10x looser there
-    tol = 2e-5 if name in ("opm", "edge_mix") else 2e-6
-    assert err[..., 0:3][pos_ok].max() <= tol * 1000.0
-    assert err[..., 3:6][ok[..., 3:6]].max() <= tol
+    hard = name in ("opm", "edge_mix")
+    if precision == "f32":
+        tol_p, tol_d, tol_ph = (2e-5 if hard else 2e-6) * 1000.0, 2e-5 if hard else 2e-6, 2e-5 if hard else 2e-6
+    else:
+        tol_p, tol_d, tol_ph = (1e-9 if hard else 1e-11) * 1000.0, 1e-10 if hard else 1e-12, 1e-10 if hard else 1e-12
+    assert err[..., 0:3][ok[..., 0:3]].max() <= tol_p
+    assert err[..., 3:6][ok[..., 3:6]].max() <= tol_d
     ph_ok = ok[..., 6]
-    assert (err[..., 6][ph_ok] <= tol * np.maximum(scale[..., 6][ph_ok], 1.0)).all()
+    assert (err[..., 6][ph_ok] <= tol_ph * np.maximum(scale[..., 6][ph_ok], 1.0)).all()
     assert np.array_equal(got[..., 7][ok[..., 7]], want[..., 7][ok[..., 7]])
 
 

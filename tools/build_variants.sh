@@ -7,8 +7,8 @@ cd "$(dirname "$0")/../ray_trace_pb_b200/csrc"
 for spec in "$@"; do
   if [[ "$spec" =~ ^[0-9]+$ ]]; then name="mb$spec"; defs="-DRTB_TRACE_MIN_BLOCKS=$spec"; else name="${spec%%:*}"; defs="${spec#*:}"; fi
   mkdir -p ../_lib/var_$name
-  for f in rtb_api trace_f64 trace_f32 aux_kernels psf_kernels; do
-    extra="-fmad=false"; [ $f = trace_f32 ] && extra="-fmad=true -prec-div=false -prec-sqrt=false"
+  for f in rtb_api trace_f64 trace_fast aux_kernels psf_kernels; do
+    extra="-fmad=false"; [ $f = trace_fast ] && extra="-fmad=true -prec-div=false -prec-sqrt=false"
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo $extra -Xcompiler -fPIC -Xptxas -v \
       $defs -c $f.cu -o ../_lib/var_$name/$f.o 2> ../_lib/var_$name/$f.log &
   done
