@@ -345,6 +345,8 @@ def _to_device(a, device=0):
     if isinstance(a, torch.Tensor):
         return a.to(device=f"cuda:{device}", dtype=torch.float64).contiguous(), True
     arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if not arr.flags.writeable:           # e.g. a broadcast view; torch.from_numpy wants a writable buffer
+        arr = arr.copy()
     return torch.from_numpy(arr).to(f"cuda:{device}"), False
 
 
