@@ -414,6 +414,6 @@ cudaError_t run_copy_probe(long long bytes, double *bytes_per_s)
     return cudaGetLastError();
 }
 
-// fp32 mode lives in trace_f32.cu
+// the fast modes live in trace_fast.cu
 
 } // namespace rtb
