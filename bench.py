@@ -289,6 +289,28 @@ def main():
     n_valid = int(torch.isfinite(out[0, :, 0]).sum())
     stats = reducer.stats() if (reducer is not None and reducer.stats_t is not None) else None
 
+    # ---- the reference's own output mode (full (2S+1, N, 8) history), device resident: the HBM-bound regime ------
+    full_history = None
+    if rank == 0:
+        n_fh = min(n_rays, 4_000_000)
+        fh_out = torch.empty((2 * N_SURFACES + 1, n_fh, 8), dtype=torch.float64, device=f"cuda:{local}")
+        fh_in = rays[:n_fh]
+        for _ in range(2):
+            dev.trace_tensor(system.surfaces, materials, fh_in, keep="all", wavelengths=[WAVELENGTH], out=fh_out)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(5):
+            dev.trace_tensor(system.surfaces, materials, fh_in, keep="all", wavelengths=[WAVELENGTH], out=fh_out)
+        f1.record()
+        torch.cuda.synchronize()
+        fh_ms = f0.elapsed_time(f1) / 5
+        fh_bytes = n_fh * 64.0 * (2 * N_SURFACES + 2)                # 64 B in + 21 x 64 B out per ray
+        full_history = {"bound": "hbm", "achieved": fh_bytes / (fh_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": fh_bytes / (fh_ms * 1e-3) / 1e9 / hbm_peak, "rays": n_fh, "kernel_ms": fh_ms,
+                        "ray_surfaces_per_s": n_fh * N_SURFACES / (fh_ms * 1e-3),
+                        "algorithmic_bytes_per_ray": 64.0 * (2 * N_SURFACES + 2), "peak_source": hbm_src}
+        del fh_out
+
     # ---- end-to-end through the host-buffer C ABI ---------------------------------------------------------------
     n_e2e = int(args.e2e_rays)
     e2e_side = int(np.sqrt(n_e2e))
@@ -358,6 +380,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "ray*surfaces/s", "h2d_bytes_per_step": n_e2e * 64,
                     "d2h_bytes_per_step": n_e2e * 64, "rays_per_gpu_per_step": n_e2e, "steps": e2e_steps,
                     "api": "rtb_trace_host via engine.trace_host (pinned host buffers, keep='last')"},
+            "roofline_full_history": full_history,
             "dropin_full_history": dropin,
             "gpu_launches": int(launches),
             "clocks": clocks,
