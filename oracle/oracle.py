@@ -18,7 +18,6 @@ Pinning status: pinned against live outputs of the reference itself, ``tests/gol
 from __future__ import annotations
 
 import ctypes
-import os
 import subprocess
 from pathlib import Path
 

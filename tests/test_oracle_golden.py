@@ -4,7 +4,6 @@ CPU tests (no GPU): the oracle against the golden vectors written from the refer
 These are the pins the GPU parity tests rest on: if oracle/rt_oracle.c drifts from the reference's arithmetic,
 this file fails before any CUDA result is trusted.
 """
-import json
 
 import numpy as np
 import pytest

@@ -14,7 +14,6 @@ if len(sys.argv) == 1:
 
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
-import numpy as np  # noqa: E402
 import bench  # noqa: E402
 from ray_trace_pb_b200 import _ffi, engine  # noqa: E402
 
