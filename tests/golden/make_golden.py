@@ -111,6 +111,21 @@ def main():
                         "system": systems.describe_system(system, m_in, m_out)}
         print(f"{name:22s} N={rays.shape[0]:6d} NaN at end={checks[name]['nan_rays_at_end']:6d}  oracle == reference")
 
+    # ------------------------------------------------------------------ random systems (checksums only)
+    rand = {}
+    for seed in range(systems.N_RANDOM_SYSTEMS):
+        system, m_in, m_out, rays = systems.random_system(rt, rtm, seed)
+        with np.errstate(all="ignore"):
+            hist = system.ray_trace(rays, m_in, m_out)
+        got = oracle.ray_trace(system, rays, m_in, m_out)
+        parity.assert_bit_identical(got, hist, f"oracle vs reference, random system {seed}")
+        kinds = "".join(type(s_).__name__[0] + type(s_).__name__[-1] for s_ in system.surfaces)
+        rand[str(seed)] = {"sha256_history": parity.digest(hist), "n_surfaces": len(system.surfaces), "kinds": kinds,
+                           "alive_at_end": int(np.isfinite(hist[-1, :, 0]).sum())}
+    checks_random = rand
+    print(f"random systems         {len(rand)} seeds, alive at end: "
+          f"{[v['alive_at_end'] for v in rand.values()]}  oracle == reference")
+
     # ------------------------------------------------------------------ intersect_rays
     rng = np.random.default_rng(5)
     system, m_in, m_out, rays = systems.relay10_script(rt, rtm)
@@ -197,7 +212,8 @@ def main():
     np.savez_compressed(HERE / "ray2plane.npz", rays=g1[:6], out=p2p, ts=ts)
     (HERE / "host_api.json").write_text(json.dumps(host, indent=1))
 
-    (HERE / "checksums.json").write_text(json.dumps({"cases": summary, "big": checks}, indent=1))
+    (HERE / "checksums.json").write_text(json.dumps({"cases": summary, "big": checks, "random": checks_random},
+                                                    indent=1))
     print("wrote", HERE)
 
 

@@ -409,6 +409,65 @@ def reversed_doublet(rt, rtm, n_disps=21, nphis=4):
     return system, rtm.Vacuum(), rtm.Vacuum(), rays
 
 
+def random_system(rt, rtm, seed: int, n_rays: int = 1500):
+    """
+    A random sequential system (3-10 surfaces of all four kinds, random glasses, decentred / tilted elements) and a
+    random ray bundle.  Built from a seeded PCG64 stream and + - * / sqrt only, so it is the same on every platform:
+    make_golden.py records the sha256 of the REFERENCE's history for each seed, tests re-derive it.
+    """
+    rng = np.random.default_rng(1000 + seed)
+    glasses = [rtm.Vacuum, lambda: rtm.Constant(1.33), rtm.Bk7, rtm.Sf10, rtm.Nlak22, rtm.FusedSilica, rtm.Nsf6,
+               lambda: rtm.Constant(1.0)]
+
+    def unit(v):
+        v = np.asarray(v, dtype=float)
+        return v / np.sqrt((v * v).sum())
+
+    n_surf = int(rng.integers(3, 11))
+    surfaces, z = [], 0.0
+    for k in range(n_surf):
+        kind = rng.choice(["sphere", "sphere", "sphere", "flat", "flat", "lens", "mirror"]) if k == n_surf - 1 else \
+            rng.choice(["sphere", "sphere", "sphere", "flat", "flat", "lens"])
+        off = rng.uniform(-1.5, 1.5, 2) * (rng.random() < 0.5)
+        aperture = float(rng.uniform(5.0, 15.0))
+        if kind == "sphere":
+            radius = float(rng.uniform(20.0, 200.0) * (1 if rng.random() < 0.5 else -1))
+            surfaces.append(rt.SphericalSurface(radius, [off[0], off[1], z + radius], aperture))
+        else:
+            tilt = rng.uniform(-0.08, 0.08, 2) * (rng.random() < 0.5)
+            normal = unit([tilt[0], tilt[1], 1.0]) if tilt.any() else np.array([0.0, 0.0, 1.0])
+            if kind == "flat":
+                surfaces.append(rt.FlatSurface([off[0], off[1], z], normal, aperture))
+            elif kind == "mirror":
+                surfaces.append(rt.PlaneMirror([off[0], off[1], z], normal, aperture))
+            else:
+                surfaces.append(rt.PerfectLens(float(rng.uniform(20.0, 100.0)), [off[0], off[1], z], normal,
+                                               float(rng.uniform(0.2, 0.6))))
+        z += float(rng.uniform(2.0, 30.0))
+    pick = lambda: glasses[int(rng.integers(0, len(glasses)))]()
+    system = rt.System(surfaces, [pick() for _ in range(n_surf - 1)])
+    m_in, m_out = pick(), pick()
+
+    rays = np.zeros((n_rays, 8))
+    r = 8.0 * np.sqrt(rng.random(n_rays))
+    c = unit(rng.standard_normal((2, n_rays)).T[0])  # unused draw keeps the stream simple to reason about
+    del c
+    ang = rng.standard_normal((n_rays, 2))
+    ang = ang / np.sqrt((ang * ang).sum(axis=1, keepdims=True))
+    rays[:, 0] = r * ang[:, 0]
+    rays[:, 1] = r * ang[:, 1]
+    rays[:, 2] = -10.0
+    d = rng.standard_normal((n_rays, 3)) * np.array([0.06, 0.06, 0.0]) + np.array([0.0, 0.0, 1.0])
+    rays[:, 3:6] = d / np.sqrt((d * d).sum(axis=1, keepdims=True))
+    rays[:, 6] = rng.uniform(0, 50, n_rays)
+    rays[:, 7] = rng.choice(rng.uniform(0.4, 1.1, 3), size=n_rays)
+    rays[rng.integers(0, n_rays, 5)] = np.nan
+    return system, m_in, m_out, rays
+
+
+N_RANDOM_SYSTEMS = 40
+
+
 CASES = {
     "plano_convex": plano_convex,
     "plano_convex_3d": lambda rt, rtm: plano_convex(rt, rtm, n_disps=31, nphis=8),

@@ -74,6 +74,16 @@ def test_big_batch_checksum(name, rt, rtm, checksums):
     assert parity.digest(last[0]) == ref["sha256_last"]
 
 
+@pytest.mark.parametrize("seed", range(systems.N_RANDOM_SYSTEMS))
+def test_random_systems_checksum(seed, rt, rtm, checksums):
+    """40 random systems: the GPU history hashes to the sha256 recorded from the reference itself"""
+    system, m_in, m_out, rays = systems.random_system(rt, rtm, seed)
+    ref = checksums["random"][str(seed)]
+    hist = system.ray_trace(rays, m_in, m_out)
+    assert int(np.isfinite(hist[-1, :, 0]).sum()) == ref["alive_at_end"]
+    assert parity.digest(hist) == ref["sha256_history"]
+
+
 # ------------------------------------------------------------------------------------------------ vs the oracle
 def _fuzz_rays(n, seed, zlo=-8.0, spread=0.35):
     rng = np.random.default_rng(seed)

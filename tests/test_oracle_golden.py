@@ -61,6 +61,17 @@ def test_oracle_big_batch_checksum(name, rt, rtm, oracle, checksums):
     assert parity.digest(hist[-1]) == ref["sha256_last"]
 
 
+@pytest.mark.parametrize("seed", range(systems.N_RANDOM_SYSTEMS))
+def test_oracle_random_systems(seed, rt, rtm, oracle, checksums):
+    """40 random systems (all surface kinds, decentred / tilted, random glasses): sha256 of the reference's history"""
+    system, m_in, m_out, rays = systems.random_system(rt, rtm, seed)
+    ref = checksums["random"][str(seed)]
+    assert len(system.surfaces) == ref["n_surfaces"]
+    hist = oracle.ray_trace(system, rays, m_in, m_out)
+    assert int(np.isfinite(hist[-1, :, 0]).sum()) == ref["alive_at_end"]
+    assert parity.digest(hist) == ref["sha256_history"]
+
+
 def test_oracle_threads_do_not_change_results(rt, rtm, oracle):
     g = load_golden("edge_mix")
     system, m_in, m_out = systems.rebuild_system(g["system"], rt, rtm)
