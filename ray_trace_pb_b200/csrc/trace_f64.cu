@@ -15,7 +15,10 @@
 //   * divisions by one denominator share the Newton-refined reciprocal (exact_math.cuh: same bits as IEEE `/`);
 //   * `norm <= aperture` and `|norm - |R|| < 1e-12` are tested on the squared sum against host-computed exact
 //     thresholds (monotonicity of the correctly rounded sqrt), so those square roots are never taken;
-//   * the NaN fills of culled rays are applied once, where a slab is stored or feeds the next surface.
+//   * the NaN fills of culled rays are applied once, where a slab is stored or feeds the next surface;
+//   * each surface runs branch-free ("Optimistic") with one domain flag and is redone by the self-checking
+//     ("Careful") instantiation when the flag fails; terms multiplied by the exact zeros of a z-aligned normal or
+//     axis are dropped when all operands are known finite (surface_steps.cuh).
 #include <cmath>
 #include <math_constants.h>
 
@@ -31,7 +34,7 @@ namespace {
 // per-block shared prescription-derived constants
 struct SharedConsts {
     double rcp_radius[kMaxSurfaces]; // refined 1/R per spherical surface (1/f for perfect lenses)
-    unsigned long long rcp_ok;       // bit k: den_ok of that denominator
+    unsigned long long rcp_ok;       // bit k: that reciprocal is usable by the Optimistic steps (see below)
 };
 
 // ---- the kernel --------------------------------------------------------------------------------------------
