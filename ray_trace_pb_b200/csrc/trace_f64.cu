@@ -115,41 +115,76 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
         bool force_careful = non_finite(cur.ox) | non_finite(cur.oy) | non_finite(cur.oz) | non_finite(cur.dx) |
                              non_finite(cur.dy) | non_finite(cur.dz);
         int k = 0;
-#ifdef RTB_SURFACE_UNROLL2
-#pragma unroll 2
-#else
-#pragma unroll 1
-#endif
-        for (; k < P.n_surf && !dead; k++) {
-            const DevSurface &s = P.surf[k];
-            const double n2 = !USE_TABLE ? eval_index(P.mat[k + 1], wl0)
-                                         : (unlisted ? index_for_unlisted(&P.mat[k + 1], wl0) : s_ntab[row + k + 1]);
-            // what this surface's two slabs are needed for (uniform): bit 0 store "at", 1 store "after",
-            // 2 reduce "at", 3 reduce "after"
-            const int act = GENERAL ? P.slab_act[k] : 0;
-            const bool need_at = (act & 5) != 0;
-            auto emit_at = [&](const Ray &at) {
-                if (act & 1) store_ray(P.out + P.slab_pos[2 * k + 1] * P.out_stride, i, out_rows, planes_out, at);
-                if (act & 4) reduce_sample(P.red, at, tally);
-            };
-            xm::Rcp rcp_k;
-            rcp_k.b = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
-            rcp_k.y = s_c.rcp_radius[k];
-            rcp_k.ok = (s_c.rcp_ok >> k) & 1ull;
-            // run the surface optimistically; one flag says whether every intermediate stayed in the fast
-            // paths' domain, otherwise redo this surface with the Careful arithmetic (surface_steps.cuh)
+        double n2 = n1;
+        auto index_after = [&](int kk) {
+            return !USE_TABLE ? eval_index(P.mat[kk + 1], wl0)
+                              : (unlisted ? index_for_unlisted(&P.mat[kk + 1], wl0) : s_ntab[row + kk + 1]);
+        };
+        auto radius_rcp = [&](const DevSurface &s, int kk) {
+            xm::Rcp r;
+            r.b = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
+            r.y = s_c.rcp_radius[kk];
+            r.ok = (s_c.rcp_ok >> kk) & 1ull;
+            return r;
+        };
+        // One surface with nothing to keep.  It runs optimistically; one flag says whether every intermediate stayed
+        // in the fast paths' domain, otherwise the surface is redone with the Careful arithmetic (surface_steps.cuh).
+        auto plain_surface = [&](int kk) {
+            const DevSurface &s = P.surf[kk];
+            n2 = index_after(kk);
+            const xm::Rcp rcp_k = radius_rcp(s, kk);
             Optimistic m;
             m.ok = !force_careful;
             force_careful = false;
             AtRaw raw;
             Ray after;
             if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {
-                const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + k] : xm::div(n1, n2);
-                // two instantiations so that the at-surface values are only kept alive where they are consumed
-                dead = need_at ? refracting_step<Optimistic, true>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only,
-                                                                   raw, after)
-                               : refracting_step<Optimistic, false>(m, s, cur, n1, ratio, rcp_wl, rcp_k,
-                                                                    !intersect_only, raw, after);
+                const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + kk] : xm::div(n1, n2);
+                dead = refracting_step<Optimistic, false>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only, raw,
+                                                          after);
+                if (!m.ok) {
+                    const StepResult redo = careful_refracting(&s, cur, n1, ratio, !intersect_only);
+                    after = redo.after;
+                    dead = redo.dead;
+                }
+            } else if (s.kind == RTB_SURF_MIRROR) {
+                dead = mirror_step<Optimistic, false>(m, s, cur, n1, rcp_wl, raw, after);
+                if (!m.ok) {
+                    const StepResult redo = careful_mirror(&s, cur, n1);
+                    after = redo.after;
+                    dead = redo.dead;
+                }
+            } else {
+                dead = perfect_lens_step<Optimistic>(m, s, cur, n1, n2, rcp_wl, rcp_k, intersect_only, false, raw, after);
+                if (!m.ok) {
+                    const StepResult redo = careful_lens(&s, cur, n1, n2, intersect_only);
+                    after = redo.after;
+                    dead = redo.dead;
+                }
+            }
+            cur = after;
+            n1 = n2;
+        };
+        // One surface with a stored or reduced slab.  act (uniform): bit 0 store "at", 1 store "after", 2 reduce
+        // "at", 3 reduce "after".
+        auto observed_surface = [&](int kk, int act) {
+            const DevSurface &s = P.surf[kk];
+            n2 = index_after(kk);
+            const xm::Rcp rcp_k = radius_rcp(s, kk);
+            const bool need_at = (act & 5) != 0;
+            auto emit_at = [&](const Ray &at) {
+                if (act & 1) store_ray(P.out + P.slab_pos[2 * kk + 1] * P.out_stride, i, out_rows, planes_out, at);
+                if (act & 4) reduce_sample(P.red, at, tally);
+            };
+            Optimistic m;
+            m.ok = !force_careful;
+            force_careful = false;
+            AtRaw raw;
+            Ray after;
+            if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {
+                const double ratio = (USE_TABLE && !unlisted) ? s_ratio[row + kk] : xm::div(n1, n2);
+                dead = refracting_step<Optimistic, true>(m, s, cur, n1, ratio, rcp_wl, rcp_k, !intersect_only, raw,
+                                                         after);
                 if (!m.ok) {
                     const StepResult redo = careful_refracting(&s, cur, n1, ratio, !intersect_only);
                     if (need_at) emit_at(redo.at);
@@ -157,8 +192,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                     dead = redo.dead;
                 }
             } else if (s.kind == RTB_SURF_MIRROR) {
-                dead = need_at ? mirror_step<Optimistic, true>(m, s, cur, n1, rcp_wl, raw, after)
-                               : mirror_step<Optimistic, false>(m, s, cur, n1, rcp_wl, raw, after);
+                dead = mirror_step<Optimistic, true>(m, s, cur, n1, rcp_wl, raw, after);
                 if (!m.ok) {
                     const StepResult redo = careful_mirror(&s, cur, n1);
                     if (need_at) emit_at(redo.at);
@@ -180,14 +214,28 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                 fill_at(raw, cur, at);
                 emit_at(at);
             }
-            if (GENERAL && (act & 10)) {
+            if (act & 10) {
                 Ray out = after;
                 if (dead) set_nan(out); // the optimistic step leaves a culled ray's values un-blanked
-                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, i, out_rows, planes_out, out);
+                if (act & 2) store_ray(P.out + P.slab_pos[2 * kk + 2] * P.out_stride, i, out_rows, planes_out, out);
                 if (act & 8) reduce_sample(P.red, out, tally);
             }
             cur = after;
             n1 = n2;
+        };
+        if (!GENERAL) {
+#pragma unroll 1
+            for (; k < P.n_surf && !dead; k++) plain_surface(k);
+        } else {
+            // runs of surfaces with nothing to keep go through the same tight loop as the final-slab-only kernel
+            while (k < P.n_surf && !dead) {
+#pragma unroll 1
+                for (; k < P.n_surf && !dead && P.slab_act[k] == 0; k++) plain_surface(k);
+                if (k < P.n_surf && !dead) {
+                    observed_surface(k, P.slab_act[k]);
+                    k++;
+                }
+            }
         }
         if (GENERAL && dead) {
             // blank what is left of a dead ray's history (reductions skip NaN samples, nothing to add there)
