@@ -41,7 +41,11 @@ typedef struct {
 
 static const double ORC_PI = 3.141592653589793; /* np.pi */
 
-static double dot3(const double *a, const double *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+/* xp.sum(a * b, axis=1) of (N,3) rows.  numpy's add.reduce starts from the identity +0.0, so three products that are
+ * all -0 sum to +0 (measured on numpy 2.3.5 for every N: np.sum([[-0., -0., -0.]], axis=1) == [+0.]); for any other
+ * operands this is (a0 b0 + a1 b1) + a2 b2.  Sums the reference writes out as a + b + c (propagate_ray2plane,
+ * SphericalSurface.get_intersect) have no such start value and are spelled inline below. */
+static double dot3(const double *a, const double *b) { return ((0.0 + a[0] * b[0]) + a[1] * b[1]) + a[2] * b[2]; }
 
 /* np.linalg.norm(x, axis=1): sqrt(add.reduce(x*x)) */
 static double norm3(const double *a) { return sqrt((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]); }

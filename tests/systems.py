@@ -329,6 +329,35 @@ def perfect_imaging(rt, rtm, n_thetas=31, nphis=9, dz=0.002):
     return system, rtm.Vacuum(), rtm.Vacuum(), rays
 
 
+def perfect_imaging_in_focus(rt, rtm, n_thetas=21, nphis=8):
+    """the textbook bundle: point source exactly at the front focal point (focal-plane height exactly 0), hence a beam
+    exactly along the axis into the second lens (transverse direction exactly 0)"""
+    wavelength = 0.532e-3
+    na, f1, f2 = 0.3, 3.0, 30.0
+    alpha = np.arcsin(na)
+    system = rt.System([rt.PerfectLens(f1, [0, 0, f1], [0, 0, 1], alpha),
+                        rt.FlatSurface([0, 0, 2 * f1], [0, 0, 1], 3 * f1),
+                        rt.PerfectLens(f2, [0, 0, 2 * f1 + f2], [0, 0, 1], alpha),
+                        rt.FlatSurface([0, 0, 2 * f1 + 2 * f2], [0, 0, 1], 10.)],
+                       [rtm.Vacuum(), rtm.Vacuum(), rtm.Vacuum()])
+    rays = rt.get_ray_fan([0.0, 0.0, 0.0], 1.2 * alpha, n_thetas, wavelength, nphis=nphis)
+    return system, rtm.Vacuum(), rtm.Vacuum(), rays
+
+
+def retro_mirror(rt, rtm, n=15, nphis=8):
+    """a collimated beam sent straight back by a mirror (exactly normal incidence on mirror and windows), then a
+    second, tilted bundle"""
+    system = rt.System([rt.FlatSurface([0, 0, 0], [0, 0, 1], 25.0),
+                        rt.PlaneMirror([0, 0, 30], [0, 0, -1], 25.0),
+                        rt.FlatSurface([0, 0, 10], [0, 0, -1], 25.0),
+                        rt.SphericalSurface(-80.0, [0, 0, 5.0 - 80.0], 25.0, input_axis=(0, 0, -1))],
+                       [rtm.Bk7(), rtm.Bk7(), rtm.Constant(1.3)])
+    a = rt.get_collimated_rays([0, 0, -5], 12.0, n, 0.6, nphis=nphis)
+    ang = 0.05
+    b = rt.get_collimated_rays([0, 0, -5], 12.0, n, 0.6, nphis=nphis, normal=[np.sin(ang), 0, np.cos(ang)])
+    return system, rtm.Vacuum(), rtm.Vacuum(), np.concatenate((a, b), axis=0)
+
+
 def cauchy_singlet(rt, rtm, n=200, seed=7):
     """a user-defined medium (overridden n) with one wavelength per ray drawn from 5 lines"""
     Cauchy = make_cauchy(rtm)
@@ -465,6 +494,49 @@ def random_system(rt, rtm, seed: int, n_rays: int = 1500):
     return system, m_in, m_out, rays
 
 
+def launched_on_plane(rt, rtm, which, n=400, seed=77):
+    """
+    Rays that start exactly on the first (plane) surface, t = +-0 there, as when a script puts its source on the flat
+    at z = 0; zero components of both signs in positions, directions, phases and normals, so the sign of every exact
+    zero is exercised.  `which`: 0 flat +z, 1 flat with normal (-0, 0, -1), 2 tilted flat, 3 mirror, 4 perfect lens.
+    """
+    rng = np.random.default_rng(seed + which)
+    zero = np.array([0.0, -0.0])
+    tilt = np.array([np.sin(0.2), 0.0, np.cos(0.2)])
+    first = [lambda: rt.FlatSurface([0, 0, 0], [0, 0, 1], 30.0),
+             lambda: rt.FlatSurface([0, 0, 0], [-0.0, 0.0, -1.0], 30.0),
+             lambda: rt.FlatSurface([0, 0, 0], tilt, 30.0),
+             lambda: rt.PlaneMirror([0, 0, 0], [0.0, -0.0, 1.0], 30.0),
+             lambda: rt.PerfectLens(20.0, [0, 0, 0], [0, 0, 1], 0.6)][which]()
+    back = which in (1, 3)   # light leaves these towards -z
+    system = rt.System([first, rt.SphericalSurface.get_on_axis(40.0, -5.0 if back else 5.0, 25.0),
+                        rt.FlatSurface([0, 0, -9.0 if back else 9.0], [0, 0, -1.0 if back else 1.0], 25.0)],
+                       [rtm.Bk7(), rtm.Constant(1.5)])
+    if back:
+        system.surfaces[1].input_axis = -system.surfaces[1].input_axis
+        system.surfaces[1].output_axis = -system.surfaces[1].output_axis
+    rays = np.zeros((n, 8))
+    rays[:, 0:2] = rng.uniform(-3, 3, (n, 2))
+    rays[: n // 4, 0] = rng.choice(zero, n // 4)
+    rays[n // 8: n // 2, 1] = rng.choice(zero, n // 2 - n // 8)
+    if which == 2:   # points of the tilted plane through the origin
+        rays[:, 2] = -rays[:, 0] * tilt[0] / tilt[2]
+        rays[::3, 0] = rng.choice(zero, len(rays[::3]))
+        rays[::3, 2] = rng.choice(zero, len(rays[::3]))
+    else:
+        rays[:, 2] = rng.choice(zero, n)
+    d = rng.normal(0, 0.15, (n, 3))
+    d[:, 2] = -1.0 if which == 1 else 1.0
+    d[::5, 0] = rng.choice(zero, len(d[::5]))
+    d[::7, 1] = rng.choice(zero, len(d[::7]))
+    d[::10, 0:2] = rng.choice(zero, (len(d[::10]), 2))
+    d[::11, 2] *= -1
+    rays[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 6] = rng.choice(np.array([0.0, -0.0, 1.5, -2.0]), n)
+    rays[:, 7] = 0.532
+    return system, rtm.Vacuum(), rtm.Vacuum(), rays
+
+
 N_RANDOM_SYSTEMS = 40
 
 
@@ -484,6 +556,13 @@ CASES = {
     "edge_mix": edge_mix,
     "reversed_doublet": reversed_doublet,
     "invalid_inputs": invalid_inputs,
+    "perfect_imaging_in_focus": perfect_imaging_in_focus,
+    "retro_mirror": retro_mirror,
+    "on_plane_flat": lambda rt, rtm: launched_on_plane(rt, rtm, 0),
+    "on_plane_flat_back": lambda rt, rtm: launched_on_plane(rt, rtm, 1),
+    "on_plane_tilted": lambda rt, rtm: launched_on_plane(rt, rtm, 2),
+    "on_plane_mirror": lambda rt, rtm: launched_on_plane(rt, rtm, 3),
+    "on_plane_lens": lambda rt, rtm: launched_on_plane(rt, rtm, 4),
 }
 
 # cases whose refractive indices go through np.power (Ebaf11) and are therefore only bit-reproducible on a host

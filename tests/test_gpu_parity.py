@@ -127,6 +127,34 @@ def test_partially_invalid_input_rays_vs_oracle(rt, rtm, oracle):
         parity.assert_bit_identical(got, want, builder.__name__)
 
 
+def test_rays_launched_on_a_plane_vs_oracle(rt, rtm, oracle):
+    """t = +-0 at the first surface (the reference's scripts put the source on a flat at z = 0); signs of zeros count"""
+    for which in range(5):
+        system, m_in, m_out, rays = systems.launched_on_plane(rt, rtm, which, n=30_000, seed=1234)
+        got = system.ray_trace(rays, m_in, m_out)
+        want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+        parity.assert_bit_identical(got, want, f"launched on plane {which}")
+        assert np.isfinite(want[-1, :, 0]).mean() > 0.5
+
+
+def test_degenerate_bundles_stay_on_the_fast_path_and_match(rt, rtm, oracle, torch, dev):
+    """beams along the axis / sources at the focus: exactly normal incidence on planes, exactly zero transverse
+    direction and focal-plane height in perfect lenses -- whole bundles of them, at a size where a slow path shows"""
+    wl = 0.6
+    system, m_in, m_out, _ = systems.retro_mirror(rt, rtm)
+    rays = rt.get_collimated_rays([0, 0, -5], 12.0, 300, wl, nphis=200)
+    got = system.ray_trace(rays, m_in, m_out)
+    want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+    parity.assert_bit_identical(got, want, "retro mirror")
+    assert np.isfinite(want[-1]).all()
+    system, m_in, m_out, _ = systems.perfect_imaging_in_focus(rt, rtm)
+    rays = rt.get_ray_fan([0.0, 0.0, 0.0], 0.25, 300, 0.532e-3, nphis=200)
+    got = system.ray_trace(rays, m_in, m_out)
+    want = oracle.ray_trace(system, rays, m_in, m_out, n_threads=8)
+    parity.assert_bit_identical(got, want, "perfect imaging, source at the focus")
+    assert np.isfinite(want[-1]).all()
+
+
 def test_fuzz_opm_vs_oracle(rt, rtm, oracle):
     system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
     rays = rt.get_ray_fan([1e-3, -2e-3, 5e-4], 1.05 * alpha1, 301, 532e-6, nphis=97)
