@@ -64,6 +64,37 @@ def beam_source(n_rays_total: int):
     return RaySource.grid([0, 0, 0], 12.0, side, WAVELENGTH, n_v=side), side
 
 
+def link_probe(torch, device: int, nbytes: int = 1 << 28):
+    """Host<->device copy rates of THIS box (pinned memory, GB/s): the ceiling of the host-buffer path.  The boxes
+    of the pool differ by almost 2x here (virtualised PCIe), so `e2e` is only meaningful next to this."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}")
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}")
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_in, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_b, non_blocking=True)
+
+    def best(fn, moved):
+        t = 1e30
+        for _ in range(3):
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(device)
+            t = min(t, time.perf_counter() - t0)
+        return moved / t / 1e9
+
+    return {"h2d_gbps": best(h2d, nbytes), "d2h_gbps": best(d2h, nbytes),
+            "both_gbps": best(lambda: (h2d(), d2h()), 2 * nbytes)}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -335,6 +366,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = float(e2e_src.n_rays) * N_SURFACES * e2e_steps / float(te[0])
     assert np.isfinite(host_out[0, n_e2e // 2, 0])
+    link = link_probe(torch, local) if rank == 0 else None
 
     # the unmodified reference call: System.ray_trace(numpy rays) -> full (2S+1, N, 8) history in host memory
     dropin = None
@@ -379,7 +411,9 @@ def main():
                                  "frac": BYTES_PER_RAY * rays_per_s_gpu / 1e9 / hbm_peak, "peak_source": hbm_src}},
             "e2e": {"value": e2e_value, "unit": "ray*surfaces/s", "h2d_bytes_per_step": n_e2e * 64,
                     "d2h_bytes_per_step": n_e2e * 64, "rays_per_gpu_per_step": n_e2e, "steps": e2e_steps,
-                    "api": "rtb_trace_host via engine.trace_host (pinned host buffers, keep='last')"},
+                    "api": "rtb_trace_host via engine.trace_host (pinned host buffers, keep='last')",
+                    "link": link,
+                    "link_frac": (e2e_value / world / N_SURFACES * 128 / 1e9) / link["both_gbps"]},
             "roofline_full_history": full_history,
             "dropin_full_history": dropin,
             "gpu_launches": int(launches),

@@ -165,8 +165,14 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             cur = after;
             n1 = n2;
         };
-        // One surface with a stored or reduced slab.  act (uniform): bit 0 store "at", 1 store "after", 2 reduce
-        // "at", 3 reduce "after".
+        // act (uniform per surface): bit 0 store "at", 1 store "after", 2 reduce "at", 3 reduce "after"
+        auto emit_after = [&](int kk, int act) {
+            Ray out = cur;
+            if (dead) set_nan(out); // the optimistic step leaves a culled ray's values un-blanked
+            if (act & 2) store_ray(P.out + P.slab_pos[2 * kk + 2] * P.out_stride, i, out_rows, planes_out, out);
+            if (act & 8) reduce_sample(P.red, out, tally);
+        };
+        // One surface whose "at" slab is stored or reduced.
         auto observed_surface = [&](int kk, int act) {
             const DevSurface &s = P.surf[kk];
             n2 = index_after(kk);
@@ -214,12 +220,6 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                 fill_at(raw, cur, at);
                 emit_at(at);
             }
-            if (act & 10) {
-                Ray out = after;
-                if (dead) set_nan(out); // the optimistic step leaves a culled ray's values un-blanked
-                if (act & 2) store_ray(P.out + P.slab_pos[2 * kk + 2] * P.out_stride, i, out_rows, planes_out, out);
-                if (act & 8) reduce_sample(P.red, out, tally);
-            }
             cur = after;
             n1 = n2;
         };
@@ -227,12 +227,18 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
 #pragma unroll 1
             for (; k < P.n_surf && !dead; k++) plain_surface(k);
         } else {
-            // runs of surfaces with nothing to keep go through the same tight loop as the final-slab-only kernel
+            // runs of surfaces whose "at" slab is not needed go through the same tight loop as the final-slab-only kernel
             while (k < P.n_surf && !dead) {
 #pragma unroll 1
-                for (; k < P.n_surf && !dead && P.slab_act[k] == 0; k++) plain_surface(k);
+                for (; k < P.n_surf && !dead && (P.slab_act[k] & 5) == 0; k++) {
+                    plain_surface(k);
+                    const int act = P.slab_act[k];
+                    if (act & 10) emit_after(k, act);
+                }
                 if (k < P.n_surf && !dead) {
-                    observed_surface(k, P.slab_act[k]);
+                    const int act = P.slab_act[k];
+                    observed_surface(k, act);
+                    if (act & 10) emit_after(k, act);
                     k++;
                 }
             }
