@@ -11,5 +11,6 @@ QI2lab/ray_trace_pb.
 ``device``     device-resident API (torch tensors as HBM buffers, ray sources, fused reductions)
 ``sharding``   ray-range sharding over the GPUs of one node and the NCCL all-reduce of reduced products
 ``engine``     prescription packing                       ``_ffi``       ctypes binding of librtb.so (include/rtb.h)
+``analysis``   spot / pupil / focus sweeps on the device  ``persist``    sweep results in the scripts' zarr layout
 """
 __version__ = "0.1.0"

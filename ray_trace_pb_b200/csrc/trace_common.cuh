@@ -64,13 +64,27 @@ __device__ __forceinline__ double linspace_at(long long i, long long n, double s
     return (n > 1 && i == n - 1) ? stop : v;
 }
 
+// idx = hi * n + lo with 0 <= lo < n; 32-bit division when both fit (the 64-bit one is a ~100-instruction routine)
+__device__ __forceinline__ void split_index(long long idx, long long n, long long &lo, long long &hi)
+{
+    if ((((unsigned long long)idx | (unsigned long long)n) >> 32) == 0) {
+        const unsigned q = (unsigned)idx / (unsigned)n;
+        hi = q;
+        lo = (unsigned)idx - q * (unsigned)n;
+    } else {
+        hi = idx / n;
+        lo = idx - hi * n;
+    }
+}
+
 __device__ __noinline__ Ray make_ray(const DevSource &g, long long idx)
 {
     Ray r;
     r.ph = 0.0;
     r.wl = g.wavelength;
     if (g.kind == RTB_SRC_GRID) {
-        const long long iu = idx % g.n_a, iv = idx / g.n_a;
+        long long iu, iv;
+        split_index(idx, g.n_a, iu, iv);
         const double u = linspace_at(iu, g.n_a, g.a_start, g.a_step, g.a_stop);
         const double v = linspace_at(iv, g.n_b, g.b_start, g.b_step, g.b_stop);
         r.ox = __dadd_rn(__dadd_rn(g.px, __dmul_rn(g.e1x, u)), __dmul_rn(g.e2x, v));
@@ -78,7 +92,8 @@ __device__ __noinline__ Ray make_ray(const DevSource &g, long long idx)
         r.oz = __dadd_rn(__dadd_rn(g.pz, __dmul_rn(g.e1z, u)), __dmul_rn(g.e2z, v));
         r.dx = g.axx; r.dy = g.axy; r.dz = g.axz;
     } else if (g.kind == RTB_SRC_COLLIMATED) {
-        const long long ip = idx % g.n_b, id = idx / g.n_b;
+        long long ip, id;
+        split_index(idx, g.n_b, ip, id);
         const double off = linspace_at(id, g.n_a, g.a_start, g.a_step, g.a_stop);
         const double phi = __dadd_rn(__dmul_rn((double)ip, kTwoPi) / (double)g.n_b, g.b_start);
         double sp, cp;
@@ -89,7 +104,8 @@ __device__ __noinline__ Ray make_ray(const DevSource &g, long long idx)
         r.oz = __dadd_rn(__dadd_rn(g.pz, __dmul_rn(g.e1z, a)), __dmul_rn(g.e2z, b));
         r.dx = g.axx; r.dy = g.axy; r.dz = g.axz;
     } else {
-        const long long it = idx % g.n_a, ip = idx / g.n_a;
+        long long it, ip;
+        split_index(idx, g.n_a, it, ip);
         const double theta = linspace_at(it, g.n_a, g.a_start, g.a_step, g.a_stop);
         const double phi = ((double)ip * kTwoPi) / (double)g.n_b;
         double st, ct, sp, cp;
