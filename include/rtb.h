@@ -239,6 +239,19 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
 int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first_ray, int64_t n_rays,
                      double *out_dev, const rtb_trace_opts *opts, int device, void *stream);
 
+/*
+ * A sweep in ONE launch (field points, wavelengths, defocus ... : the loops of the reference's scripts, e.g.
+ * scripts/2022_08_24_relay_astigmatism.py:83-92, scripts/2022_08_04_ACT508-100-B.py:95-110): n_src sources, each
+ * tracing ray indices [first_ray, first_ray + n_rays_each) of its own index space through the same system.
+ * Source k's rays occupy rows [k * n_rays_each, (k + 1) * n_rays_each) of every output slab (out_dev is
+ * (n_out_slabs, n_src * n_rays_each, 8)), and its reductions go to bucket k of opts->reduce: statistics at
+ * stats_dev + k * RTB_N_STATS, grid at grid_dev + k * 3 * grid_n * grid_n (initialise every bucket with
+ * rtb_reduce_init).  sys must tabulate the sources' wavelengths (at most RTB_MAX_WAVELENGTHS distinct ones; more are
+ * fine when every medium is CONSTANT / SELLMEIER).
+ */
+int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_src, int64_t first_ray,
+                      int64_t n_rays_each, double *out_dev, const rtb_trace_opts *opts, int device, void *stream);
+
 /* ---- ray sources: replace get_collimated_rays / get_ray_fan, raytrace.py:45-161 --------------------------- */
 int rtb_generate_device(const rtb_source *src, int64_t first_ray, int64_t n_rays, double *rays_out_dev,
                         int device, void *stream);

@@ -84,7 +84,7 @@ _lib = None
 
 # every symbol include/rtb.h declares (tests check the .so exports all of them)
 EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_count", "rtb_trace_device",
-           "rtb_trace_host", "rtb_trace_source", "rtb_generate_device", "rtb_reduce_init",
+           "rtb_trace_host", "rtb_trace_source", "rtb_trace_sources", "rtb_generate_device", "rtb_reduce_init",
            "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
            "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
            "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device"]
@@ -108,6 +108,8 @@ def lib():
     L.rtb_trace_host.argtypes = [C.POINTER(RtbSystem), vp, i64, vp, C.POINTER(RtbTraceOpts), i32]
     L.rtb_trace_source.argtypes = [C.POINTER(RtbSystem), C.POINTER(RtbSource), i64, i64, vp,
                                    C.POINTER(RtbTraceOpts), i32, vp]
+    L.rtb_trace_sources.argtypes = [C.POINTER(RtbSystem), C.POINTER(RtbSource), i32, i64, i64, vp,
+                                    C.POINTER(RtbTraceOpts), i32, vp]
     L.rtb_generate_device.argtypes = [C.POINTER(RtbSource), i64, i64, vp, i32, vp]
     L.rtb_reduce_init.argtypes = [C.POINTER(RtbReduce), i32, vp]
     L.rtb_intersect_rays_device.argtypes = [vp, i64, vp, i64, vp, i32, vp]
@@ -127,7 +129,8 @@ def lib():
     L.rtb_host_alloc.restype = vp
     L.rtb_host_free.argtypes = [vp]
     L.rtb_host_free.restype = None
-    for name in ("rtb_trace_device", "rtb_trace_host", "rtb_trace_source", "rtb_generate_device", "rtb_reduce_init",
+    for name in ("rtb_trace_device", "rtb_trace_host", "rtb_trace_source", "rtb_trace_sources", "rtb_generate_device",
+                 "rtb_reduce_init",
                  "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
                  "rtb_ray2plane_device", "rtb_distinct_wavelengths_device"):
         getattr(L, name).restype = i32

@@ -52,7 +52,9 @@ def spot_statistics(system, initial_material, final_material, sources, slab: int
     Spot statistics of one or several ray bundles at slab ``slab`` (default: at the last surface, the scripts'
     ``rays[-2]``): for each :class:`~ray_trace_pb_b200.device.RaySource` a dict with ``count``, ``centroid``,
     ``rms_radius``, ``mean_phase``, ``rms_phase``, ``u_range``, ``v_range``.  ``origin`` defaults to the centre of the
-    surface the slab belongs to.  One fused kernel launch per source chunk; no ray I/O.
+    surface the slab belongs to.  No ray I/O: sources of equal size (a field or wavelength sweep) are traced by ONE
+    fused generate-trace-reduce launch (``dev.trace_sources``, one reduction bucket per source); otherwise one launch
+    per source chunk, spread over streams.
     """
     single = isinstance(sources, dev.RaySource)
     sources = [sources] if single else list(sources)
@@ -61,6 +63,10 @@ def spot_statistics(system, initial_material, final_material, sources, slab: int
     if origin is None:
         origin = system.surfaces[max(slab - 1, 0) // 2].center
     mats = _materials(system, initial_material, final_material)
+    if len(sources) > 1 and len({src.n_rays for src in sources}) == 1 and sources[0].n_rays <= chunk:
+        red = dev.Reducer(slab, origin=origin, e1=e1, e2=e2, device=device, buckets=len(sources))
+        dev.trace_sources(system.surfaces, mats, sources, keep="none", precision=precision, reducer=red, device=device)
+        return red.stats()
     run = _Launcher(system, mats, device)
     reducers = []
     for src in sources:

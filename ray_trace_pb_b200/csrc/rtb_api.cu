@@ -72,6 +72,7 @@ struct DeviceCtx {
     int sm_count = 0;
     Slot slot[kSlots];
     std::mutex host_path; // one host-buffer trace at a time per device
+    cudaMemPool_t pool = nullptr; // small stream-ordered allocations (sweep source lists); keeps its memory
 };
 
 constexpr int kMaxDevices = 64;
@@ -306,6 +307,9 @@ int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TracePar
         P.slab_act[k] = (uint8_t)act;
     }
     P.src.kind = -1;
+    P.src_list = nullptr;
+    P.n_src = 0;
+    P.pad1 = 0;
     return RTB_OK;
 }
 
@@ -443,6 +447,60 @@ int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first
     P.n_rays = n_rays;
     P.out_stride = 8 * (long long)n_rays;
     return launch(P, opts->precision, ctx->sm_count, (cudaStream_t)stream);
+}
+
+int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_src, int64_t first_ray,
+                      int64_t n_rays_each, double *out_dev, const rtb_trace_opts *opts, int device, void *stream)
+{
+    rtb::TraceParams P;
+    int rc = pack_params(sys, opts, P);
+    if (rc) return rc;
+    if (!srcs) return fail(RTB_ERR_INVALID, "source list pointer is NULL");
+    if (n_src < 1 || n_src > 65535) return fail(RTB_ERR_INVALID, "n_src = %d, expected 1 .. 65535", n_src);
+    if (opts->flags & RTB_FLAG_PLANES_IN) return fail(RTB_ERR_INVALID, "RTB_FLAG_PLANES_IN has no meaning for sources");
+    std::vector<rtb::DevSource> list((size_t)n_src);
+    for (int k = 0; k < n_src; k++)
+        if ((rc = pack_source(srcs + k, first_ray, n_rays_each, list[(size_t)k]))) return rc;
+    if (n_rays_each == 0) return RTB_OK;
+    if (P.any_store && !out_dev) return fail(RTB_ERR_INVALID, "out_dev is NULL but the keep mode stores rays");
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the list lives in stream-ordered device memory for exactly this launch (pageable source: the copy has staged
+    // it by the time the call returns, so the vector may go out of scope)
+    rtb::DevSource *list_dev = nullptr;
+    const size_t bytes = sizeof(rtb::DevSource) * (size_t)n_src;
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        if (!ctx->pool) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            RTB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+            unsigned long long keep = ~0ull;    // never hand the (few KB of) memory back between calls
+            RTB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+    }
+    if (cudaMallocFromPoolAsync((void **)&list_dev, bytes, ctx->pool, st) != cudaSuccess)
+        return fail(RTB_ERR_NOMEM, "stream-ordered allocation of %zu bytes for the source list failed", bytes);
+    cudaError_t e = cudaMemcpyAsync(list_dev, list.data(), bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(list_dev, st);
+        return fail(RTB_ERR_CUDA, "copying the source list failed: %s", cudaGetErrorString(e));
+    }
+    P.src = list[0];
+    P.src_list = list_dev;
+    P.n_src = n_src;
+    P.rays_in = nullptr;
+    P.out = out_dev;
+    P.n_rays = n_rays_each;
+    P.out_stride = 8 * (long long)n_rays_each * n_src;
+    rc = launch(P, opts->precision, ctx->sm_count, st);
+    cudaFreeAsync(list_dev, st);
+    return rc;
 }
 
 int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_rays, double *out_host,

@@ -104,6 +104,11 @@ struct TraceParams {
     uint8_t slab_act[kMaxSurfaces];  // per surface: bit 0 store at-slab, 1 store after-slab, 2 reduce at, 3 reduce after
     DevReduce red;
     DevSource src;
+    // a sweep (rtb_trace_sources): n_src > 0 sources in global memory, one per blockIdx.y, each tracing n_rays rays
+    // into rows [y * n_rays, (y + 1) * n_rays) of the output and into bucket y of the reductions
+    const DevSource *src_list;
+    int32_t n_src;
+    int32_t pad1;
     DevSurface surf[kMaxSurfaces];
     DevMaterial mat[kMaxMedia];
     double wl[kMaxWavelengths];

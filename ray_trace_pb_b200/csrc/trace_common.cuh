@@ -119,6 +119,33 @@ __device__ __noinline__ Ray make_ray(const DevSource &g, long long idx)
     return r;
 }
 
+// ---- sweeps (rtb_trace_sources): the block's source and reduction bucket, staged in shared memory ------------------
+template <bool SWEEP>
+struct SweepShared {
+    char unused;
+};
+template <>
+struct SweepShared<true> {
+    DevSource src;
+    DevReduce red;
+};
+
+__device__ __forceinline__ void sweep_setup(const TraceParams &, SweepShared<false> &) {}
+__device__ __forceinline__ const DevSource &sweep_source(const TraceParams &P, const SweepShared<false> &) { return P.src; }
+__device__ __forceinline__ const DevReduce &sweep_reduce(const TraceParams &P, const SweepShared<false> &) { return P.red; }
+__device__ __forceinline__ const DevSource &sweep_source(const TraceParams &, const SweepShared<true> &s) { return s.src; }
+__device__ __forceinline__ const DevReduce &sweep_reduce(const TraceParams &, const SweepShared<true> &s) { return s.red; }
+
+__device__ __forceinline__ void sweep_setup(const TraceParams &P, SweepShared<true> &s)
+{
+    if (threadIdx.x == 0) {
+        s.src = P.src_list[blockIdx.y];
+        s.red = P.red;
+        if (s.red.stats) s.red.stats += (long long)blockIdx.y * RTB_N_STATS;
+        if (s.red.grid) s.red.grid += (long long)blockIdx.y * 3 * s.red.grid_n * s.red.grid_n;
+    }
+}
+
 // ---- fused reductions (rtb_reduce in rtb.h) -----------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v)
 {

@@ -40,14 +40,20 @@ struct SharedConsts {
 // ---- the kernel --------------------------------------------------------------------------------------------
 // USE_TABLE   refractive indices (and n1/n2) from the host table (any material), else in-register Sellmeier.
 // FROM_SOURCE rays are produced by the on-device source instead of being read from memory.
-// MODE        0: only the final slab is stored; 1: general (any slab selection, fused reductions).
+// MODE        0: only the final slab is stored; 1: general (any slab selection, fused reductions); 2: general, as a
+//             sweep over P.n_src sources (FROM_SOURCE only): blockIdx.y picks the source, its output rows and its
+//             reduction bucket.
 template <bool USE_TABLE, bool FROM_SOURCE, int MODE>
 __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kernel(const __grid_constant__ TraceParams P)
 {
-    constexpr bool GENERAL = MODE == 1;
+    constexpr bool GENERAL = MODE >= 1;
+    constexpr bool SWEEP = MODE == 2;
+    static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
     __shared__ double s_ntab[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     __shared__ double s_ratio[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     __shared__ SharedConsts s_c;
+    __shared__ SweepShared<SWEEP> s_sweep;
+    if (SWEEP) sweep_setup(P, s_sweep);     // visible after the first __syncthreads below
     const int n_med = P.n_surf + 1;
     if (USE_TABLE) {
         const int count = (P.n_wl + 1) * n_med;
@@ -68,6 +74,9 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
     }
     __syncthreads();
 
+    const DevSource &source = sweep_source(P, s_sweep);
+    const DevReduce &red = sweep_reduce(P, s_sweep);
+    const long long row0 = SWEEP ? (long long)blockIdx.y * P.n_rays : 0;
     const bool reducing = GENERAL && P.red.slab >= 0;
     const bool intersect_only = GENERAL && (P.flags & RTB_FLAG_INTERSECT_ONLY) != 0;
     Tally tally;
@@ -79,7 +88,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_rays; i += stride) {
         Ray cur;
         if (FROM_SOURCE)
-            cur = make_ray(P.src, P.src.first + i);
+            cur = make_ray(source, source.first + i);
         else
             load_ray(P.rays_in, i, P.n_rays, planes_in, cur);
 
@@ -99,8 +108,8 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             row *= n_med;
         }
         if (GENERAL) {
-            if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, i, out_rows, planes_out, cur);
-            if (reducing && P.red.slab == 0) reduce_sample(P.red, cur, tally);
+            if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, row0 + i, out_rows, planes_out, cur);
+            if (reducing && P.red.slab == 0) reduce_sample(red, cur, tally);
         }
 
         double n1 = !USE_TABLE ? eval_index(P.mat[0], wl0)
@@ -169,8 +178,8 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
         auto emit_after = [&](int kk, int act) {
             Ray out = cur;
             if (dead) set_nan(out); // the optimistic step leaves a culled ray's values un-blanked
-            if (act & 2) store_ray(P.out + P.slab_pos[2 * kk + 2] * P.out_stride, i, out_rows, planes_out, out);
-            if (act & 8) reduce_sample(P.red, out, tally);
+            if (act & 2) store_ray(P.out + P.slab_pos[2 * kk + 2] * P.out_stride, row0 + i, out_rows, planes_out, out);
+            if (act & 8) reduce_sample(red, out, tally);
         };
         // One surface whose "at" slab is stored or reduced.
         auto observed_surface = [&](int kk, int act) {
@@ -179,8 +188,8 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             const xm::Rcp rcp_k = radius_rcp(s, kk);
             const bool need_at = (act & 5) != 0;
             auto emit_at = [&](const Ray &at) {
-                if (act & 1) store_ray(P.out + P.slab_pos[2 * kk + 1] * P.out_stride, i, out_rows, planes_out, at);
-                if (act & 4) reduce_sample(P.red, at, tally);
+                if (act & 1) store_ray(P.out + P.slab_pos[2 * kk + 1] * P.out_stride, row0 + i, out_rows, planes_out, at);
+                if (act & 4) reduce_sample(red, at, tally);
             };
             Optimistic m;
             m.ok = !force_careful;
@@ -250,8 +259,8 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
 #pragma unroll 1
             for (; k < P.n_surf; k++) {
                 const int act = P.slab_act[k];
-                if (act & 1) store_ray(P.out + P.slab_pos[2 * k + 1] * P.out_stride, i, out_rows, planes_out, blank);
-                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, i, out_rows, planes_out, blank);
+                if (act & 1) store_ray(P.out + P.slab_pos[2 * k + 1] * P.out_stride, row0 + i, out_rows, planes_out, blank);
+                if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, row0 + i, out_rows, planes_out, blank);
             }
         }
         if (!GENERAL) {
@@ -259,13 +268,13 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             store_ray(P.out, i, out_rows, planes_out, cur);
         }
     }
-    if (GENERAL && reducing) tally_flush(P.red, tally);
+    if (GENERAL && reducing) tally_flush(red, tally);
 }
 
 template <bool T, bool S, int M>
 cudaError_t launch_one(const TraceParams &P, unsigned blocks, cudaStream_t stream)
 {
-    trace_f64_kernel<T, S, M><<<blocks, kTraceThreads, 0, stream>>>(P);
+    trace_f64_kernel<T, S, M><<<dim3(blocks, M == 2 ? (unsigned)P.n_src : 1u), kTraceThreads, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -277,10 +286,15 @@ cudaError_t launch_trace_f64(const TraceParams &P, int sm_count, cudaStream_t st
     if (P.n_rays <= 0) return cudaSuccess;
     long long blocks = (P.n_rays + kTraceThreads - 1) / kTraceThreads;
     // a whole number of waves over the SMs, grid-stride inside
-    const long long max_blocks = (long long)sm_count * kTraceMinBlocks * 4;
+    long long max_blocks = (long long)sm_count * kTraceMinBlocks * 4;
+    const bool sweep = P.n_src > 0;
+    if (sweep) max_blocks = (max_blocks + P.n_src - 1) / P.n_src;   // the cap is for the whole grid
     if (blocks > max_blocks) blocks = max_blocks;
     const bool table = P.n_wl > 0;
     const bool source = P.src.kind >= 0;
+    if (sweep)
+        return table ? launch_one<true, true, 2>(P, (unsigned)blocks, stream)
+                     : launch_one<false, true, 2>(P, (unsigned)blocks, stream);
     const bool fast = P.store_last_only && P.red.slab < 0 && (P.flags & RTB_FLAG_INTERSECT_ONLY) == 0;
     const unsigned b = (unsigned)blocks;
     if (fast) {

@@ -190,15 +190,19 @@ __device__ __forceinline__ bool lens_step(const DevSurface &s, const RayT<T> &in
     return culled;
 }
 
-template <typename T, bool USE_TABLE, bool FROM_SOURCE>
+// SWEEP (FROM_SOURCE only): blockIdx.y picks the source, its output rows and its reduction bucket (rtb_trace_sources)
+template <typename T, bool USE_TABLE, bool FROM_SOURCE, bool SWEEP = false>
 __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel(const __grid_constant__ TraceParams P)
 {
+    static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
     __shared__ double s_ntab[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     __shared__ double s_ratio[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
     // per-surface fp32 constants and the fp32 copy of n1/n2, converted once per block (conversions run on the
     // quarter-rate XU pipe, so they must not be repeated per ray)
     __shared__ T s_geo[kMaxSurfaces][8];   // normal xyz, axis xyz, 1/R, aperture^2 (unused slot)
     __shared__ T s_ratio_f[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
+    __shared__ SweepShared<SWEEP> s_sweep;
+    if (SWEEP) sweep_setup(P, s_sweep);     // visible after the __syncthreads below
     const int n_med = P.n_surf + 1;
     if (USE_TABLE) {
         const int count = (P.n_wl + 1) * n_med;
@@ -216,6 +220,9 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
         s_geo[k][7] = (T)0;
     }
     __syncthreads();
+    const DevSource &source = sweep_source(P, s_sweep);
+    const DevReduce &red = sweep_reduce(P, s_sweep);
+    const long long row0 = SWEEP ? (long long)blockIdx.y * P.n_rays : 0;
     const bool reducing = P.red.slab >= 0;
     const bool intersect_only = (P.flags & RTB_FLAG_INTERSECT_ONLY) != 0;
     Tally tally;
@@ -227,11 +234,11 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_rays; i += stride) {
         Ray first;
         if (FROM_SOURCE)
-            first = make_ray(P.src, P.src.first + i);
+            first = make_ray(source, source.first + i);
         else
             load_ray(P.rays_in, i, P.n_rays, planes_in, first);
-        if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, i, out_rows, planes_out, first);
-        if (reducing && P.red.slab == 0) reduce_sample(P.red, first, tally);
+        if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, row0 + i, out_rows, planes_out, first);
+        if (reducing && P.red.slab == 0) reduce_sample(red, first, tally);
 
         // the ray, in registers: position / phase fp64, direction fp32; the wavelength only ever turns NaN with the
         // whole ray (dead)
@@ -260,8 +267,8 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
             const int act = P.slab_act[q];
             auto emit = [&](bool at_slab, const Ray &w) {
                 const int pos = P.slab_pos[2 * q + (at_slab ? 1 : 2)];
-                if (act & (at_slab ? 1 : 2)) store_ray(P.out + pos * P.out_stride, i, out_rows, planes_out, w);
-                if (act & (at_slab ? 4 : 8)) reduce_sample(P.red, w, tally);
+                if (act & (at_slab ? 1 : 2)) store_ray(P.out + pos * P.out_stride, row0 + i, out_rows, planes_out, w);
+                if (act & (at_slab ? 4 : 8)) reduce_sample(red, w, tally);
             };
             if (dead) {
                 if (act) {
@@ -352,7 +359,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
             n1 = n2;
         }
     }
-    if (reducing) tally_flush(P.red, tally);
+    if (reducing) tally_flush(red, tally);
 }
 
 template <typename T>
@@ -360,6 +367,14 @@ cudaError_t launch_fast(const TraceParams &P, unsigned b, int threads, cudaStrea
 {
     const bool table = P.n_wl > 0;
     const bool source = P.src.kind >= 0;
+    if (P.n_src > 0) {
+        const dim3 grid(b, (unsigned)P.n_src);
+        if (table)
+            trace_fast_kernel<T, true, true, true><<<grid, threads, 0, stream>>>(P);
+        else
+            trace_fast_kernel<T, false, true, true><<<grid, threads, 0, stream>>>(P);
+        return cudaGetLastError();
+    }
     if (table && source)
         trace_fast_kernel<T, true, true><<<b, threads, 0, stream>>>(P);
     else if (table)
@@ -378,7 +393,8 @@ cudaError_t launch_trace_fast(const TraceParams &P, int precision, int sm_count,
     if (P.n_rays <= 0) return cudaSuccess;
     const int threads = 128;
     long long blocks = (P.n_rays + threads - 1) / threads;
-    const long long max_blocks = (long long)sm_count * 32;
+    long long max_blocks = (long long)sm_count * 32;
+    if (P.n_src > 0) max_blocks = (max_blocks + P.n_src - 1) / P.n_src;   // the cap is for the whole grid
     if (blocks > max_blocks) blocks = max_blocks;
     return precision == RTB_F64_FAST ? launch_fast<double>(P, (unsigned)blocks, threads, stream)
                                      : launch_fast<float>(P, (unsigned)blocks, threads, stream);

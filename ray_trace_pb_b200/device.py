@@ -234,6 +234,43 @@ def trace_source(surfaces, materials, source: RaySource, first: int = 0, count: 
     return out
 
 
+def trace_sources(surfaces, materials, sources, first: int = 0, count: int | None = None, keep="none",
+                  precision="f64", reducer=None, device: int = 0, out=None, packed=None):
+    """
+    A sweep in ONE launch (kernel grid y = source): every ``RaySource`` of ``sources`` -- field points, wavelengths,
+    defocused object points ... -- generates rays [first, first+count) of its own index space and traces them through
+    the same system.  Source k fills rows [k*count, (k+1)*count) of every kept slab (``out`` is
+    ``(n_kept, len(sources)*count, 8)``) and bucket k of ``reducer`` (create it with ``buckets=len(sources)``).
+    The sources must have the same number of rays; their wavelengths are tabulated together (at most 8 distinct ones
+    unless every medium has a closed formula).
+    """
+    torch = _torch()
+    _ffi.require_device()
+    sources = list(sources)
+    if not sources:
+        raise ValueError("no sources")
+    if len({s.n_rays for s in sources}) != 1:
+        raise ValueError("the sources of one sweep launch must have the same number of rays")
+    count = sources[0].n_rays - first if count is None else count
+    if reducer is not None and reducer.buckets != len(sources):
+        raise ValueError(f"reducer has {reducer.buckets} bucket(s), the sweep has {len(sources)} sources")
+    if packed is None:
+        wls = sorted({float(s.wavelength) for s in sources if np.isfinite(s.wavelength)})
+        packed = _system_for(surfaces, materials, wls or None)
+    mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
+    opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
+    if n_out == 0:
+        out = None
+    elif out is None:
+        out = torch.empty((n_out, len(sources) * count, 8), dtype=torch.float64, device=f"cuda:{device}")
+    arr = (_ffi.RtbSource * len(sources))(*[s.struct for s in sources])
+    rc = _ffi.lib().rtb_trace_sources(C.byref(packed.sys), arr, len(sources), first, count,
+                                      out.data_ptr() if out is not None else None, C.byref(opts), device,
+                                      _stream_ptr(device))
+    _ffi.check(rc)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 # fused reductions
 # ----------------------------------------------------------------------------------------------------------
@@ -245,17 +282,25 @@ class Reducer:
     (3, G, G) tensor: sum cos(phase - phase_ref), sum sin(phase - phase_ref), count (indexed [plane, iv, iu]).
     Accumulates across calls until :meth:`reset`.  ``allreduce()`` sums over the ranks of the default
     ``torch.distributed`` group (NCCL over NVLink): the only communication of a multi-GPU trace.
+    ``buckets`` > 1 makes one set per source of a sweep (:func:`trace_sources`): ``stats_t`` is (buckets, 12) and
+    ``grid_t`` (buckets, 3, G, G).
     """
 
     def __init__(self, slab: int, origin=(0, 0, 0), e1=(1, 0, 0), e2=(0, 1, 0), grid_n: int = 0,
-                 half_width: float = 1.0, phase_ref: float = 0.0, stats: bool = True, device: int = 0):
+                 half_width: float = 1.0, phase_ref: float = 0.0, stats: bool = True, device: int = 0,
+                 buckets: int = 1):
         torch = _torch()
         _ffi.require_device()
+        if buckets < 1:
+            raise ValueError("buckets must be >= 1")
         self.device = device
         self.slab = int(slab)
         self.grid_n = int(grid_n)
-        self.stats_t = torch.empty(_ffi.RTB_N_STATS, dtype=torch.float64, device=f"cuda:{device}") if stats else None
-        self.grid_t = (torch.empty((3, grid_n, grid_n), dtype=torch.float64, device=f"cuda:{device}")
+        self.buckets = int(buckets)
+        lead = (self.buckets,) if self.buckets > 1 else ()
+        self.stats_t = (torch.empty(lead + (_ffi.RTB_N_STATS,), dtype=torch.float64, device=f"cuda:{device}")
+                        if stats else None)
+        self.grid_t = (torch.empty(lead + (3, grid_n, grid_n), dtype=torch.float64, device=f"cuda:{device}")
                        if grid_n > 0 else None)
         s = _ffi.RtbReduce()
         s.slab = self.slab
@@ -277,8 +322,14 @@ class Reducer:
         return self
 
     def reset(self):
-        rc = _ffi.lib().rtb_reduce_init(C.byref(self.struct), self.device, _stream_ptr(self.device))
-        _ffi.check(rc)
+        for b in range(self.buckets):
+            one = _ffi.RtbReduce()
+            C.memmove(C.byref(one), C.byref(self.struct), C.sizeof(one))
+            if self.stats_t is not None:
+                one.stats_dev = self.stats_t.data_ptr() + b * _ffi.RTB_N_STATS * 8
+            if self.grid_t is not None:
+                one.grid_dev = self.grid_t.data_ptr() + b * 3 * self.grid_n * self.grid_n * 8
+            _ffi.check(_ffi.lib().rtb_reduce_init(C.byref(one), self.device, _stream_ptr(self.device)))
 
     def allreduce(self):
         from .sharding import allreduce_grid, allreduce_stats
@@ -288,7 +339,7 @@ class Reducer:
             allreduce_stats(self.stats_t)
         return self
 
-    def psf(self, n_samples: int, df: float, normalize_by_count: bool = False, field: bool = False):
+    def psf(self, n_samples: int, df: float, normalize_by_count: bool = False, field: bool = False, bucket: int = 0):
         """
         PSF from the accumulated pupil grid as a zoomed DFT (kernel zgemm_nt_kernel): ``n_samples x n_samples`` samples
         of |E|^2, E = A P B^T, at spatial frequencies (k - (n-1)/2) * df along u (columns) and v (rows).  For a lens
@@ -305,17 +356,25 @@ class Reducer:
         out = torch.empty((n_samples, n_samples), dtype=torch.float64, device=dev)
         f_re = torch.empty_like(out) if field else None
         f_im = torch.empty_like(out) if field else None
-        rc = L.rtb_psf_from_grid_device(self.grid_t.data_ptr(), self.grid_n, float(self.struct.grid_half_width),
+        if not 0 <= bucket < self.buckets:
+            raise IndexError(f"bucket {bucket} of {self.buckets}")
+        grid_ptr = self.grid_t.data_ptr() + bucket * 3 * self.grid_n * self.grid_n * 8
+        rc = L.rtb_psf_from_grid_device(grid_ptr, self.grid_n, float(self.struct.grid_half_width),
                                         n_samples, float(df), int(normalize_by_count), scratch.data_ptr(), need,
                                         out.data_ptr(), f_re.data_ptr() if field else None,
                                         f_im.data_ptr() if field else None, self.device, _stream_ptr(self.device))
         _ffi.check(rc)
         return (out, torch.complex(f_re, f_im)) if field else out
 
-    def stats(self) -> dict:
-        """Host copy of the statistics with the derived centroid / RMS radius / RMS wavefront error."""
+    def stats(self, bucket: int | None = None):
+        """Host copy of the statistics with the derived centroid / RMS radius / RMS wavefront error (a list with one
+        entry per bucket for a sweep reducer, unless ``bucket`` picks one)."""
         v = self.stats_t.cpu().numpy()
-        return summarize_stats(v)
+        if self.buckets == 1:
+            return summarize_stats(v)
+        if bucket is not None:
+            return summarize_stats(v[bucket])
+        return [summarize_stats(row) for row in v]
 
     @property
     def grid(self):

@@ -408,6 +408,50 @@ def test_sources_generate_and_fused_trace(kind, rt, rtm, oracle, dev):
 
 
 # ------------------------------------------------------------------------------------------------ reductions
+def test_sweep_in_one_launch_equals_per_source_launches(rt, rtm, oracle, dev, torch):
+    """rtb_trace_sources: field x wavelength sweep, grid y = source; rows, statistics and grids per source"""
+    system = systems.relay10_system(rt, rtm)
+    vac = rtm.Vacuum()
+    mats = [vac] + list(system.materials) + [vac]
+    sources = []
+    for k, (th, wl) in enumerate([(0.0, 0.785), (0.004, 0.785), (0.009, 0.65), (0.013, 0.9), (0.017, 0.785)]):
+        nrm = np.array([np.sin(th), 0.0, np.cos(th)])
+        sources.append(dev.RaySource.grid([0, 0, 0], 12.0, 61, wl, normal=nrm / np.linalg.norm(nrm)))
+    n = sources[0].n_rays
+    slab = 12
+    for precision in ("f64", "f64_fast", "f32"):
+        red = dev.Reducer(slab, origin=(8.0, 0, 0), grid_n=64, half_width=8.0, buckets=len(sources))
+        out = dev.trace_sources(system.surfaces, mats, sources, keep=[0, slab, -1], precision=precision, reducer=red)
+        assert out.shape == (3, len(sources) * n, 8)
+        stats = red.stats()
+        for k, src in enumerate(sources):
+            one = dev.Reducer(slab, origin=(8.0, 0, 0), grid_n=64, half_width=8.0)
+            ref = dev.trace_source(system.surfaces, mats, src, keep=[0, slab, -1], precision=precision, reducer=one)
+            got = out[:, k * n:(k + 1) * n]
+            parity.assert_bit_identical(got.cpu().numpy(), ref.cpu().numpy(), f"sweep rows of source {k} ({precision})")
+            a, b = stats[k]["raw"], one.stats()["raw"]
+            assert a[0] == b[0] and a[0] > 0
+            np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-9)
+            np.testing.assert_allclose(red.grid[k].cpu().numpy(), one.grid.cpu().numpy(), rtol=0, atol=1e-9)
+            assert red.grid[k][2].sum().item() == one.grid[2].sum().item()
+        if precision == "f64":       # and against the oracle on the generated rays
+            rays = out[0].cpu().numpy()
+            want = oracle.ray_trace(system, rays, vac, vac, n_threads=8)
+            parity.assert_bit_identical(out[2].cpu().numpy(), want[-1], "sweep final slab vs oracle")
+    # a reducer with the wrong number of buckets, sources of different sizes
+    with pytest.raises(ValueError):
+        dev.trace_sources(system.surfaces, mats, sources, reducer=dev.Reducer(slab))
+    with pytest.raises(ValueError):
+        dev.trace_sources(system.surfaces, mats, sources[:1] + [dev.RaySource.grid([0, 0, 0], 12.0, 9, 0.785)])
+    # analysis.spot_statistics takes the single-launch route for equal-size sources: same numbers as one by one
+    from ray_trace_pb_b200 import analysis
+    many = analysis.spot_statistics(system, vac, vac, sources, slab=-2)
+    for k, src in enumerate(sources):
+        single = analysis.spot_statistics(system, vac, vac, src, slab=-2)
+        assert many[k]["count"] == single["count"]
+        np.testing.assert_allclose(many[k]["raw"], single["raw"], rtol=1e-11, atol=1e-9)
+
+
 def test_fused_reductions(rt, rtm, oracle, dev, torch):
     system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
     mats = [m_in] + system.materials + [m_out]
