@@ -240,8 +240,8 @@ int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first
                      double *out_dev, const rtb_trace_opts *opts, int device, void *stream);
 
 /*
- * A sweep in ONE launch (field points, wavelengths, defocus ... : the loops of the reference's scripts, e.g.
- * scripts/2022_08_24_relay_astigmatism.py:83-92, scripts/2022_08_04_ACT508-100-B.py:95-110): n_src sources, each
+ * A sweep in ONE launch (field points, wavelengths, defocus ... : the per-wavelength loop of
+ * scripts/2022_08_04_ACT508-100-B.py:120-150, BASELINE configs 2 and 3): n_src sources, each
  * tracing ray indices [first_ray, first_ray + n_rays_each) of its own index space through the same system.
  * Source k's rays occupy rows [k * n_rays_each, (k + 1) * n_rays_each) of every output slab (out_dev is
  * (n_out_slabs, n_src * n_rays_each, 8)), and its reductions go to bucket k of opts->reduce: statistics at
