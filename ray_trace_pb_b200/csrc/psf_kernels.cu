@@ -9,7 +9,7 @@
 // with x_u, y_v the cell centres and fx_k, fy_l = (k - (M-1)/2) * df spatial frequencies (for a lens of focal length f:
 // image coordinate = lambda f fx).  A "zoomed DFT": any sampling and window, no padding; for odd G, M = G and
 // df = 1/(G*cell) it is exactly fftshift(fft2(ifftshift(P))) (odd M puts a sample on the zero frequency).
-// fp64 throughout: tcgen05 has no f64 kind, so this runs on the FP64 pipe (64x64 register-tiled complex GEMM).
+// fp64 throughout: tcgen05 has no f64 kind, so this runs on the FP64 pipe (64x64 register-tiled, K-split complex GEMM).
 #include <cmath>
 #include <math_constants.h>
 
@@ -49,24 +49,30 @@ __global__ void dft_matrix_kernel(int M, int G, double df, double cell, double h
     }
 }
 
-// C[m, n] = sum_k X[m, k] * Y[n, k]   (complex, planar, row-major; X is Mx x K, Y is Ny x K)
-// abs2 != 0: write |C|^2 into c_re only.  64 x 64 tile per block, 16 x 16 threads, 4 x 4 complex accumulators each.
+// C[m, n] (+)= sum_{k in this block's K range} X[m, k] * Y[n, k]   (complex, planar, row-major; X is Mx x K, Y is Ny x K)
+// 64 x 64 tile per block, 16 x 16 threads, 4 x 4 complex accumulators each; thread (ty, tx) owns rows ty + 16 a and
+// columns tx + 16 b, so shared-memory reads are conflict-free (x: broadcast, y: consecutive doubles) and the stores
+// of a warp are contiguous.  gridDim.z splits K: the output tiles of a 257 x 2048 or 257 x 257 product are far too
+// few to fill 148 SMs (160 and 25), so each tile's K loop is shared by several blocks that add their partial sums
+// with red.global.add.f64 into a zeroed C.
 constexpr int kTile = 64, kStep = 16;
-__global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, const double *__restrict__ x_re,
-                                                       const double *__restrict__ x_im, const double *__restrict__ y_re,
-                                                       const double *__restrict__ y_im, double *__restrict__ c_re,
-                                                       double *__restrict__ c_im, int abs2)
+__global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, int k_chunk,
+                                                       const double *__restrict__ x_re, const double *__restrict__ x_im,
+                                                       const double *__restrict__ y_re, const double *__restrict__ y_im,
+                                                       double *__restrict__ c_re, double *__restrict__ c_im)
 {
     __shared__ double sxr[kStep][kTile + 1], sxi[kStep][kTile + 1], syr[kStep][kTile + 1], syi[kStep][kTile + 1];
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
     const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
+    const int k_begin = blockIdx.z * k_chunk, k_end = min(K, k_begin + k_chunk);
     double ar[4][4] = {}, ai[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += kStep) {
-        // stage 64 x 16 of X and of Y (k fastest in memory -> coalesced along k)
+    for (int k0 = k_begin; k0 < k_end; k0 += kStep) {
+        // stage 64 x 16 of X and of Y: k is fastest in memory, so 16 consecutive threads read one 128-byte row piece;
+        // the row stride of 65 doubles keeps the transposed shared-memory write conflict-free
         for (int e = threadIdx.x; e < kTile * kStep; e += 256) {
             const int r = e / kStep, kk = e % kStep;
             const int k = k0 + kk;
-            const bool kin = k < K;
+            const bool kin = k < k_end;
             const int m = m0 + r, n = n0 + r;
             sxr[kk][r] = (kin && m < Mx) ? x_re[(long long)m * K + k] : 0.0;
             sxi[kk][r] = (kin && m < Mx) ? x_im[(long long)m * K + k] : 0.0;
@@ -79,10 +85,10 @@ __global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, co
             double xr[4], xi[4], yr[4], yi[4];
 #pragma unroll
             for (int a = 0; a < 4; a++) {
-                xr[a] = sxr[kk][ty * 4 + a];
-                xi[a] = sxi[kk][ty * 4 + a];
-                yr[a] = syr[kk][tx * 4 + a];
-                yi[a] = syi[kk][tx * 4 + a];
+                xr[a] = sxr[kk][ty + 16 * a];
+                xi[a] = sxi[kk][ty + 16 * a];
+                yr[a] = syr[kk][tx + 16 * a];
+                yi[a] = syi[kk][tx + 16 * a];
             }
 #pragma unroll
             for (int a = 0; a < 4; a++)
@@ -94,15 +100,17 @@ __global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, co
         }
         __syncthreads();
     }
+    const bool split = gridDim.z > 1;
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            const int m = m0 + ty * 4 + a, n = n0 + tx * 4 + b;
+            const int m = m0 + ty + 16 * a, n = n0 + tx + 16 * b;
             if (m < Mx && n < Ny) {
                 const long long o = (long long)m * Ny + n;
-                if (abs2) {
-                    c_re[o] = fma(ar[a][b], ar[a][b], ai[a][b] * ai[a][b]);
+                if (split) {
+                    atomicAdd(c_re + o, ar[a][b]);
+                    atomicAdd(c_im + o, ai[a][b]);
                 } else {
                     c_re[o] = ar[a][b];
                     c_im[o] = ai[a][b];
@@ -111,23 +119,53 @@ __global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, co
         }
 }
 
+__global__ void abs2_kernel(const double *__restrict__ re, const double *__restrict__ im, long long n,
+                            double *__restrict__ out)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = fma(re[i], re[i], im[i] * im[i]);
+}
+
+// K split so that the grid is at least ~4 waves of blocks (each block still loops over >= 4 k-steps)
+cudaError_t launch_zgemm(int Mx, int Ny, int K, const double *x_re, const double *x_im, const double *y_re,
+                         const double *y_im, double *c_re, double *c_im, int sm_count, cudaStream_t stream, int *launches)
+{
+    const int tiles = ((Mx + kTile - 1) / kTile) * ((Ny + kTile - 1) / kTile);
+    int split = (4 * sm_count + tiles - 1) / tiles;
+    split = max(1, min(split, K / (4 * kStep)));
+    int k_chunk = ((K + split - 1) / split + kStep - 1) / kStep * kStep;
+    split = (K + k_chunk - 1) / k_chunk;
+    if (split > 1) {
+        cudaError_t e = cudaMemsetAsync(c_re, 0, sizeof(double) * (size_t)Mx * Ny, stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c_im, 0, sizeof(double) * (size_t)Mx * Ny, stream);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((Ny + kTile - 1) / kTile, (Mx + kTile - 1) / kTile, split);
+    zgemm_nt_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, c_re, c_im);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
 } // namespace
 
-// scratch layout (doubles): [0, 2MG) DFT matrix D (re, im) ; [2MG, 4MG) Wt (re, im) ; [4MG, 4MG + 2GG) normalised pupil
+// scratch layout (doubles): [0, 2MG) DFT matrix D (re, im) ; [2MG, 4MG) Wt (re, im) ; [4MG, 4MG + 2MM) the field E when
+// the caller does not take it ; then 2GG for the normalised pupil
 long long psf_scratch_doubles(int G, int M, int normalize)
 {
-    return 4LL * M * G + (normalize ? 2LL * G * G : 0LL);
+    return 4LL * M * G + 2LL * M * M + (normalize ? 2LL * G * G : 0LL);
 }
 
 cudaError_t launch_psf(const double *grid, int G, double half_width, int M, double df, int normalize, double *scratch,
                        double *psf_out, double *field_re, double *field_im, int sm_count, cudaStream_t stream, int *launches)
 {
-    const long long cells = (long long)G * G, mg = (long long)M * G;
+    const long long cells = (long long)G * G, mg = (long long)M * G, mm = (long long)M * M;
     double *d_re = scratch, *d_im = scratch + mg, *w_re = scratch + 2 * mg, *w_im = scratch + 3 * mg;
+    double *e_re = scratch + 4 * mg, *e_im = e_re + mm;
     const double *p_re = grid, *p_im = grid + cells;
     int n = 0;
     if (normalize) {
-        double *q_re = scratch + 4 * mg, *q_im = q_re + cells;
+        double *q_re = scratch + 4 * mg + 2 * mm, *q_im = q_re + cells;
         normalize_pupil_kernel<<<sm_count * 8, 256, 0, stream>>>(grid, cells, q_re, q_im);
         p_re = q_re;
         p_im = q_im;
@@ -137,17 +175,17 @@ cudaError_t launch_psf(const double *grid, int G, double half_width, int M, doub
     dft_matrix_kernel<<<sm_count * 8, 256, 0, stream>>>(M, G, df, cell, half_width, d_re, d_im);
     n++;
     // Wt[k, v] = sum_u D[k, u] P[v, u]
-    dim3 g1((G + kTile - 1) / kTile, (M + kTile - 1) / kTile);
-    zgemm_nt_kernel<<<g1, 256, 0, stream>>>(M, G, G, d_re, d_im, p_re, p_im, w_re, w_im, 0);
-    n++;
+    cudaError_t e = launch_zgemm(M, G, G, d_re, d_im, p_re, p_im, w_re, w_im, sm_count, stream, &n);
+    if (e != cudaSuccess) return e;
     // E[l, k] = sum_v D[l, v] Wt[k, v]   (square pupil grid: the same DFT matrix serves both axes)
-    dim3 g2((M + kTile - 1) / kTile, (M + kTile - 1) / kTile);
     if (field_re && field_im) {
-        zgemm_nt_kernel<<<g2, 256, 0, stream>>>(M, M, G, d_re, d_im, w_re, w_im, field_re, field_im, 0);
-        n++;
+        e_re = field_re;
+        e_im = field_im;
     }
+    e = launch_zgemm(M, M, G, d_re, d_im, w_re, w_im, e_re, e_im, sm_count, stream, &n);
+    if (e != cudaSuccess) return e;
     if (psf_out) {
-        zgemm_nt_kernel<<<g2, 256, 0, stream>>>(M, M, G, d_re, d_im, w_re, w_im, psf_out, nullptr, 1);
+        abs2_kernel<<<min((long long)sm_count * 8, (mm + 255) / 256), 256, 0, stream>>>(e_re, e_im, mm, psf_out);
         n++;
     }
     if (launches) *launches = n;
