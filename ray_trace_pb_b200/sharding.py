@@ -26,21 +26,22 @@ def shard_range(n_items: int, rank: int, world: int):
 def allreduce_stats(stats, dist=None):
     """
     Combine RTB_N_STATS vectors over the ranks of the default process group: entries 0-7 are sums, 8/10 minima,
-    9/11 maxima (include/rtb.h).  ``stats`` is a float64 torch tensor on the backend's device; modified in place.
+    9/11 maxima (include/rtb.h).  ``stats`` is a float64 torch tensor on the backend's device, (12,) or, for the
+    buckets of a sweep, (n, 12); modified in place.
     """
     if dist is None:
         import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return stats
-    sums = stats[0:8].clone()
-    mins = stats[[8, 10]].clone()
-    maxs = stats[[9, 11]].clone()
+    sums = stats[..., 0:8].contiguous()
+    mins = stats[..., [8, 10]].contiguous()
+    maxs = stats[..., [9, 11]].contiguous()
     dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     dist.all_reduce(mins, op=dist.ReduceOp.MIN)
     dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
-    stats[0:8] = sums
-    stats[8], stats[10] = mins[0], mins[1]
-    stats[9], stats[11] = maxs[0], maxs[1]
+    stats[..., 0:8] = sums
+    stats[..., [8, 10]] = mins
+    stats[..., [9, 11]] = maxs
     return stats
 
 

@@ -58,9 +58,14 @@ def _worker(rank, world, port, out_dir):
     last = oracle.trace(system.surfaces, mats, rays, keep_all=False)
     stats = torch.from_numpy(oracle.reduce_stats(last, (0, 0, 0), (1, 0, 0), (0, 1, 0)))
     grid = torch.from_numpy(oracle.reduce_grid(last, (0, 0, 0), (1, 0, 0), (0, 1, 0), 32, 21.0))
+    # the buckets of a sweep: (n, 12), merged row by row (second row: this rank's statistics with the x axis flipped)
+    flipped = torch.from_numpy(oracle.reduce_stats(last, (0, 0, 0), (-1, 0, 0), (0, 1, 0)))
+    buckets = torch.stack((stats, flipped)).clone()
     allreduce_stats(stats)
+    allreduce_stats(buckets)
     allreduce_grid(grid)
-    np.savez(Path(out_dir) / f"rank{rank}.npz", stats=stats.numpy(), grid=grid.numpy(), first=first, count=count)
+    np.savez(Path(out_dir) / f"rank{rank}.npz", stats=stats.numpy(), grid=grid.numpy(), first=first, count=count,
+             buckets=buckets.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -76,6 +81,9 @@ def test_two_rank_gloo_allreduce_matches_single_process(tmp_path, rt, rtm, oracl
     assert int(parts[0]["count"]) + int(parts[1]["count"]) == 96 * 96
     # every rank ends with the same, complete answer
     assert np.array_equal(parts[0]["stats"], parts[1]["stats"])
+    assert np.array_equal(parts[0]["buckets"][0], parts[0]["stats"])
+    b1 = parts[0]["buckets"][1]
+    assert b1[0] == parts[0]["stats"][0] and b1[8] == -parts[0]["stats"][9] and b1[9] == -parts[0]["stats"][8]
     assert np.array_equal(parts[0]["grid"], parts[1]["grid"])
     system, m_in, m_out, _ = systems.plano_convex(rt, rtm)
     mats = [m_in] + system.materials + [m_out]
