@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--e2e-rays", type=float, default=float(1 << 24))
     ap.add_argument("--reduce", default="grid", choices=["none", "stats", "grid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin each rank to its GPU's local CPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -229,6 +230,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # one process per GPU: sit on the CPUs next to that GPU before any page-locked buffer is allocated
+    from ray_trace_pb_b200.sharding import bind_to_device_cpus
+    all_cpus = os.sched_getaffinity(0)
+    bound = None if args.no_bind else bind_to_device_cpus(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -412,7 +417,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "ray*surfaces/s", "h2d_bytes_per_step": n_e2e * 64,
                     "d2h_bytes_per_step": n_e2e * 64, "rays_per_gpu_per_step": n_e2e, "steps": e2e_steps,
                     "api": "rtb_trace_host via engine.trace_host (pinned host buffers, keep='last')",
-                    "link": link,
+                    "link": link, "cpus_bound_rank0": (len(bound) if bound else None),
                     "link_frac": (e2e_value / world / N_SURFACES * 128 / 1e9) / link["both_gbps"]},
             "roofline_full_history": full_history,
             "dropin_full_history": dropin,
@@ -422,7 +427,8 @@ def main():
         if stats is not None:
             line["config"]["reduce_count"] = stats["count"]
         if not args.no_cpu_baseline and world == 1:        # the CPU baseline is reported at N = 1 only
-            cores = os.cpu_count() or 1
+            os.sched_setaffinity(0, all_cpus)               # the CPU baseline gets every core of the box again
+            cores = len(all_cpus)
             v, sample = cpu_baseline_run(cores)
             line["cpu_baseline"] = {"value": v, "unit": "ray*surfaces/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))

@@ -23,6 +23,35 @@ def shard_range(n_items: int, rank: int, world: int):
     return first, base + (1 if rank < extra else 0)
 
 
+def bind_to_device_cpus(device: int) -> list[int] | None:
+    """
+    Pin this process to the CPUs that are local to GPU ``device`` (NVML's ideal affinity: its NUMA node), so that the
+    page-locked host buffers it allocates next -- and the threads that fill them -- sit next to that GPU's PCIe root.
+    With one process per GPU on a two-socket node this keeps host<->device traffic off the socket interconnect.
+    Returns the CPU list, or None when NVML / the affinity call is unavailable (nothing is changed then).
+    """
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            token = visible.split(",")[device].strip()
+            handle = (pynvml.nvmlDeviceGetHandleByUUID(token) if token.startswith(("GPU-", "MIG-"))
+                      else pynvml.nvmlDeviceGetHandleByIndex(int(token)))
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def allreduce_stats(stats, dist=None):
     """
     Combine RTB_N_STATS vectors over the ranks of the default process group: entries 0-7 are sums, 8/10 minima,
