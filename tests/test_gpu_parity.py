@@ -452,6 +452,37 @@ def test_sweep_in_one_launch_equals_per_source_launches(rt, rtm, oracle, dev, to
         np.testing.assert_allclose(many[k]["raw"], single["raw"], rtol=1e-11, atol=1e-9)
 
 
+def test_final_slab_plus_reduction_mode(rt, rtm, oracle, dev, torch):
+    """keep="last" with a reduction on the launch rays or an "after" slab (the headline configuration): same final
+    slab as the plain trace, same reduction as with other slab selections, rays dying before / at / after the sampled
+    surface included"""
+    system, m_in, m_out, _ = systems.edge_mix(rt, rtm)
+    mats = [m_in] + list(system.materials) + [m_out]
+    rays_np = _fuzz_rays(60_000, seed=11)
+    rays = torch.from_numpy(rays_np).cuda()
+    n_slabs = 2 * len(system.surfaces) + 1
+    want_hist = oracle.ray_trace(system, rays_np, m_in, m_out, n_threads=8)
+    for slab in (0, 2, 4, n_slabs - 1):
+        fast = dev.Reducer(slab, origin=(0.5, -0.25, 0.0), grid_n=48, half_width=6.0)
+        last = dev.trace_tensor(system.surfaces, mats, rays, keep="last", reducer=fast)
+        parity.assert_bit_identical(last.cpu().numpy()[0], want_hist[-1], f"final slab with reduction at slab {slab}")
+        general = dev.Reducer(slab, origin=(0.5, -0.25, 0.0), grid_n=48, half_width=6.0)
+        dev.trace_tensor(system.surfaces, mats, rays, keep=[1, n_slabs - 1], reducer=general)     # general kernel
+        a, b = fast.stats()["raw"], general.stats()["raw"]
+        assert a[0] == b[0] and a[0] == np.isfinite(want_hist[slab][:, [0, 1, 2, 6]]).all(axis=1).sum()
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-9)
+        assert torch.equal(fast.grid[2], general.grid[2])
+        np.testing.assert_allclose(fast.grid.cpu().numpy(), general.grid.cpu().numpy(), rtol=0, atol=1e-9)
+    # from a source as well
+    src = dev.RaySource.fan([0.1, 0.0, -20.0], 0.2, 300, 0.532, nphis=64)
+    fast = dev.Reducer(4)
+    last = dev.trace_source(system.surfaces, mats, src, keep="last", reducer=fast)
+    general = dev.Reducer(4)
+    both = dev.trace_source(system.surfaces, mats, src, keep=[0, n_slabs - 1], reducer=general)
+    parity.assert_bit_identical(last.cpu().numpy()[0], both.cpu().numpy()[1], "source, final slab")
+    np.testing.assert_allclose(fast.stats()["raw"], general.stats()["raw"], rtol=1e-12, atol=1e-9)
+
+
 def test_fused_reductions(rt, rtm, oracle, dev, torch):
     system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
     mats = [m_in] + system.materials + [m_out]
