@@ -49,8 +49,11 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
     constexpr bool GENERAL = MODE >= 1;
     constexpr bool SWEEP = MODE == 2;
     static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
-    __shared__ double s_ntab[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
-    __shared__ double s_ratio[USE_TABLE ? (kMaxWavelengths + 1) * kMaxMedia : 1];
+    // the index tables are sized at launch ((n_wl + 1) * (n_surf + 1) doubles each, typically a few hundred bytes):
+    // shared memory comes out of the L1 that the kernel's spill slots live in
+    extern __shared__ double s_tables[];
+    double *const s_ntab = s_tables;
+    double *const s_ratio = s_tables + (USE_TABLE ? (P.n_wl + 1) * (P.n_surf + 1) : 0);
     __shared__ SharedConsts s_c;
     __shared__ SweepShared<SWEEP> s_sweep;
     if (SWEEP) sweep_setup(P, s_sweep);     // visible after the first __syncthreads below
@@ -283,7 +286,8 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
 template <bool T, bool S, int M>
 cudaError_t launch_one(const TraceParams &P, unsigned blocks, cudaStream_t stream)
 {
-    trace_f64_kernel<T, S, M><<<dim3(blocks, M == 2 ? (unsigned)P.n_src : 1u), kTraceThreads, 0, stream>>>(P);
+    const size_t tables = T ? 2 * sizeof(double) * (size_t)(P.n_wl + 1) * (size_t)(P.n_surf + 1) : 0;
+    trace_f64_kernel<T, S, M><<<dim3(blocks, M == 2 ? (unsigned)P.n_src : 1u), kTraceThreads, tables, stream>>>(P);
     return cudaGetLastError();
 }
 
