@@ -223,9 +223,10 @@ __device__ __noinline__ void reduce_sample(const DevReduce &R, const Ray r, Tall
             const long long plane = (long long)R.grid_n * R.grid_n;
             double s, c;
             sincos(ph, &s, &c);
-            atomicAdd(R.grid + cell, c);
-            atomicAdd(R.grid + plane + cell, s);
-            atomicAdd(R.grid + 2 * plane + cell, 1.0);
+            // the grid is always global memory: a plain reduction, no generic-address dispatch, nothing returned
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + cell), "d"(c) : "memory");
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + plane + cell), "d"(s) : "memory");
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + 2 * plane + cell), "d"(1.0) : "memory");
         }
     }
 }
