@@ -85,8 +85,8 @@ _lib = None
 # every symbol include/rtb.h declares (tests check the .so exports all of them)
 EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_count", "rtb_trace_device",
            "rtb_trace_host", "rtb_trace_source", "rtb_trace_sources", "rtb_generate_device", "rtb_reduce_init",
-           "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
-           "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
+           "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_dfma_chain_rate",
+           "rtb_measure_copy_bandwidth", "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
            "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device"]
 
 
@@ -124,6 +124,7 @@ def lib():
     L.rtb_psf_from_grid_device.argtypes = [vp, i32, C.c_double, i32, C.c_double, i32, vp, i64, vp, vp, vp, i32, vp]
     L.rtb_psf_from_grid_device.restype = i32
     L.rtb_measure_dfma_rate.argtypes = [i32, dp, dp]
+    L.rtb_measure_dfma_chain_rate.argtypes = [i32, i32, dp, dp]
     L.rtb_measure_copy_bandwidth.argtypes = [i32, i64, dp]
     L.rtb_host_alloc.argtypes = [C.c_size_t]
     L.rtb_host_alloc.restype = vp
@@ -131,8 +132,8 @@ def lib():
     L.rtb_host_free.restype = None
     for name in ("rtb_trace_device", "rtb_trace_host", "rtb_trace_source", "rtb_trace_sources", "rtb_generate_device",
                  "rtb_reduce_init",
-                 "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_copy_bandwidth",
-                 "rtb_ray2plane_device", "rtb_distinct_wavelengths_device"):
+                 "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_dfma_chain_rate",
+                 "rtb_measure_copy_bandwidth", "rtb_ray2plane_device", "rtb_distinct_wavelengths_device"):
         getattr(L, name).restype = i32
     if L.rtb_abi_version() != RTB_ABI_VERSION:
         raise RtbError(f"librtb.so ABI {L.rtb_abi_version()} != binding ABI {RTB_ABI_VERSION}; rebuild the library")

@@ -268,6 +268,29 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(double *sink, int iters
     if (r == 123.456) sink[0] = r; // never true; keeps the chains alive
 }
 
+// FP64 issue rate of latency-bound code: CHAINS independent dependent-DFMA chains per thread at the trace kernels' own
+// occupancy (7 warps per scheduler).  One chain per warp is what a ray through a surface looks like to the pipe: every
+// FP64 instruction then follows one of ANOTHER warp, which costs 3 cycles instead of 2.
+template <int CHAINS>
+__global__ void __launch_bounds__(128) dfma_chain_probe_kernel(double *sink, int iters, double m, double c)
+{
+    double a[CHAINS];
+#pragma unroll
+    for (int k = 0; k < CHAINS; k++) a[k] = 1.0 + threadIdx.x * 1e-9 + k;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int k = 0; k < CHAINS; k++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(m), "d"(c));
+        }
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < CHAINS; k++) r += a[k];
+    if (r == 123.456) sink[0] = r; // never true; keeps the chains alive
+}
+
 __global__ void copy_probe_kernel(const double4 *__restrict__ in, double4 *__restrict__ out, long long n)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -372,6 +395,40 @@ cudaError_t run_dfma_probe(int sm_count, double *dfma_per_s, double *elapsed_ms)
     if (e != cudaSuccess) return e;
     const double ops = (double)blocks * threads * (double)iters * 64.0;
     *dfma_per_s = ops / (best * 1e-3);
+    *elapsed_ms = best;
+    return cudaGetLastError();
+}
+
+cudaError_t run_dfma_chain_probe(int sm_count, int chains, double *dfma_per_s, double *elapsed_ms)
+{
+    double *sink = nullptr;
+    cudaError_t e = cudaMalloc(&sink, sizeof(double));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const int blocks = sm_count * 7, threads = 128, iters = 8192 / chains;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(t0);
+        switch (chains) {
+        case 1: dfma_chain_probe_kernel<1><<<blocks, threads>>>(sink, iters, 0.999999, 1e-9); break;
+        case 2: dfma_chain_probe_kernel<2><<<blocks, threads>>>(sink, iters, 0.999999, 1e-9); break;
+        case 4: dfma_chain_probe_kernel<4><<<blocks, threads>>>(sink, iters, 0.999999, 1e-9); break;
+        default: dfma_chain_probe_kernel<8><<<blocks, threads>>>(sink, iters, 0.999999, 1e-9); break;
+        }
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(sink);
+    if (e != cudaSuccess) return e;
+    *dfma_per_s = (double)blocks * threads * (double)iters * 16.0 * chains / (best * 1e-3);
     *elapsed_ms = best;
     return cudaGetLastError();
 }

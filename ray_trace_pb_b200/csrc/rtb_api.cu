@@ -30,6 +30,7 @@ cudaError_t launch_psf(const double *grid, int G, double half_width, int M, doub
                        double *psf_out, double *field_re, double *field_im, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t run_exact_math_selftest(unsigned long long seed, long long n, unsigned long long *bad_host, int sm_count);
 cudaError_t run_dfma_probe(int sm_count, double *dfma_per_s, double *elapsed_ms);
+cudaError_t run_dfma_chain_probe(int sm_count, int chains, double *dfma_per_s, double *elapsed_ms);
 cudaError_t run_copy_probe(long long bytes, double *bytes_per_s);
 } // namespace rtb
 
@@ -818,6 +819,22 @@ int rtb_measure_dfma_rate(int device, double *dfma_per_s, double *elapsed_ms)
     double ms = 0;
     cudaError_t e = rtb::run_dfma_probe(ctx->sm_count, dfma_per_s, &ms);
     if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "DFMA probe failed: %s", cudaGetErrorString(e));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return RTB_OK;
+}
+
+int rtb_measure_dfma_chain_rate(int device, int chains, double *dfma_per_s, double *elapsed_ms)
+{
+    if (!dfma_per_s) return fail(RTB_ERR_INVALID, "dfma_per_s is NULL");
+    if (chains != 1 && chains != 2 && chains != 4 && chains != 8) return fail(RTB_ERR_INVALID, "chains must be 1, 2, 4 or 8");
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    double ms = 0;
+    cudaError_t e = rtb::run_dfma_chain_probe(ctx->sm_count, chains, dfma_per_s, &ms);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "DFMA chain probe failed: %s", cudaGetErrorString(e));
     if (elapsed_ms) *elapsed_ms = ms;
     return RTB_OK;
 }

@@ -744,6 +744,12 @@ def test_launch_counter_and_probes():
     ms = ctypes.c_double()
     _ffi.check(L.rtb_measure_dfma_rate(0, ctypes.byref(rate), ctypes.byref(ms)))
     assert 1e12 < rate.value < 1e14, rate.value          # B200: ~1.9e13 DFMA/s nominal
+    # latency-bound issue rate: one chain per warp runs at about 2/3 of the eight-chain rate
+    one, eight = ctypes.c_double(), ctypes.c_double()
+    _ffi.check(L.rtb_measure_dfma_chain_rate(0, 1, ctypes.byref(one), ctypes.byref(ms)))
+    _ffi.check(L.rtb_measure_dfma_chain_rate(0, 8, ctypes.byref(eight), ctypes.byref(ms)))
+    assert 0.55 < one.value / eight.value < 0.85, (one.value, eight.value)
+    assert 0.8 < eight.value / rate.value < 1.1, (eight.value, rate.value)
     bw = ctypes.c_double()
     _ffi.check(L.rtb_measure_copy_bandwidth(0, 1 << 30, ctypes.byref(bw)))
     assert 1e12 < bw.value < 1.2e13, bw.value
