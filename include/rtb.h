@@ -31,6 +31,7 @@ extern "C" {
 #endif
 
 #define RTB_ABI_VERSION 1
+/* per launch (the prescription travels in the kernel parameter block); the host layer chains longer systems */
 #define RTB_MAX_SURFACES 64
 #define RTB_MAX_WAVELENGTHS 8 /* rows of the host refractive-index table (one extra row answers NaN wavelengths) */
 #define RTB_MAX_KEEP (2 * RTB_MAX_SURFACES + 1)

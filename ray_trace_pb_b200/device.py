@@ -98,6 +98,8 @@ def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelen
             wavelengths = distinct_wavelengths_tensor(probe)
         else:
             wavelengths = distinct_wavelengths_tensor(rays)
+    if len(surfaces) > _ffi.RTB_MAX_SURFACES:
+        return _trace_tensor_long(surfaces, materials, rays, keep, precision, wavelengths, reducer, out, flags, layout)
     packed = _system_for(surfaces, materials, wavelengths)
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
     opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
@@ -113,6 +115,48 @@ def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelen
     rc = _ffi.lib().rtb_trace_device(C.byref(packed.sys), rays.data_ptr(), n, out.data_ptr() if out is not None else None,
                                      C.byref(opts), dev, _stream_ptr(dev))
     _ffi.check(rc)
+    return out
+
+
+class _SegmentReducer:
+    """a Reducer seen from one segment of a long system: same buffers, slab index relative to the segment"""
+
+    def __init__(self, reducer, local_slab):
+        self.struct = engine.reduce_for_segment(reducer.struct, local_slab)
+
+
+def _trace_tensor_long(surfaces, materials, rays, keep, precision, wavelengths, reducer, out, flags, layout):
+    """A system of more than RTB_MAX_SURFACES surfaces, in segments chained on the device (engine.plan_segments)."""
+    torch = _torch()
+    planes = layout == "planes"
+    S = len(surfaces)
+    if len(materials) != S + 1:
+        raise ValueError("length of materials should be len(surfaces) + 1")
+    n_slabs = 2 * S + 1
+    kept, n_out = engine.global_keep_list(keep, n_slabs)
+    n = rays.shape[1] if planes else rays.shape[0]
+    out_shape = (n_out, 8, n) if planes else (n_out, n, 8)
+    if n_out == 0:
+        out = None
+    elif out is None:
+        out = torch.empty(out_shape, dtype=torch.float64, device=rays.device)
+    elif tuple(out.shape) != out_shape or out.dtype != torch.float64 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float64 tensor of shape {out_shape}")
+    red_slab = None
+    if reducer is not None:
+        red_slab = int(reducer.struct.slab) + (n_slabs if reducer.struct.slab < 0 else 0)
+    cur = rays
+    for a, b, local, chain, red in engine.plan_segments(S, kept, red_slab):
+        if not local and red is None:
+            continue
+        part = trace_tensor(surfaces[a:b], materials[a:b + 1], cur, keep=[l for l, _ in local] or "none",
+                            precision=precision, wavelengths=wavelengths,
+                            reducer=None if red is None else _SegmentReducer(reducer, red), flags=flags, layout=layout)
+        for j, (_, pos) in enumerate(local):
+            if pos >= 0:
+                out[pos].copy_(part[j])
+        if chain:
+            cur = part[len(local) - 1]
     return out
 
 
@@ -218,6 +262,12 @@ def trace_source(surfaces, materials, source: RaySource, first: int = 0, count: 
     torch = _torch()
     _ffi.require_device()
     count = source.n_rays - first if count is None else count
+    if packed is None and len(surfaces) > _ffi.RTB_MAX_SURFACES:
+        # longer than one launch: the rays are generated into memory and the segments chained (trace_tensor)
+        rays = source.generate(first, count, device=device)
+        return trace_tensor(surfaces, materials, rays, keep=keep, precision=precision,
+                            wavelengths=[source.wavelength] if np.isfinite(source.wavelength) else None,
+                            reducer=reducer, out=out)
     if packed is None:
         packed = _system_for(surfaces, materials, [source.wavelength] if np.isfinite(source.wavelength) else None)
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)

@@ -137,7 +137,8 @@ def pack_system(surfaces, materials, wavelengths=None) -> PackedSystem:
     if len(materials) != S + 1:
         raise ValueError("length of materials should be len(surfaces) + 1")
     if S > _ffi.RTB_MAX_SURFACES:
-        raise ValueError(f"at most {_ffi.RTB_MAX_SURFACES} surfaces per trace, got {S}")
+        raise ValueError(f"at most {_ffi.RTB_MAX_SURFACES} surfaces per launch, got {S} (trace_host / trace_tensor split "
+                         f"longer systems into segments)")
     surf_arr = (_ffi.RtbSurface * max(S, 1))(*[pack_surface(s) for s in surfaces])
     mat_arr = (_ffi.RtbMaterial * (S + 1))(*[pack_material(m) for m in materials])
     sys = _ffi.RtbSystem()
@@ -240,6 +241,87 @@ def choose_wavelength_table(materials, rays: np.ndarray):
     return uniq if uniq.size else None
 
 
+# ----------------------------------------------------------------------------------------------------------
+# systems longer than one launch
+# ----------------------------------------------------------------------------------------------------------
+def global_keep_list(keep, n_slabs: int):
+    """-> (sorted list of the trace's slab indices that are returned, n_out)"""
+    mode, idx, n_out = resolve_keep(keep, n_slabs)
+    if mode == _ffi.KEEP_ALL:
+        return list(range(n_slabs)), n_out
+    if mode == _ffi.KEEP_LAST:
+        return [n_slabs - 1], n_out
+    if mode == _ffi.KEEP_NONE:
+        return [], n_out
+    return [int(k) for k in idx], n_out
+
+
+def plan_segments(n_surfaces: int, kept_slabs, reduce_slab=None, width: int | None = None):
+    """
+    A kernel launch carries at most RTB_MAX_SURFACES surfaces in its parameter block; the reference has no such limit
+    (its loop, raytrace.py:657-659, just keeps appending slabs).  Longer systems are traced in segments: segment
+    [a, b) starts from the last slab of the previous one -- exactly what the reference's loop hands to the next
+    surface -- and contributes the trace's slabs 2a+1 .. 2b (the first segment also slab 0).
+
+    Returns a list of ``(a, b, local, chain, local_reduce_slab)``: ``local`` = [(slab index inside the segment,
+    position in the output or -1)], in increasing order; ``chain`` says the segment's last slab feeds the next one
+    (it is then always the last entry of ``local``); ``local_reduce_slab`` is the fused reduction's slab inside
+    this segment or None.
+    """
+    width = _ffi.RTB_MAX_SURFACES if width is None else int(width)
+    position = {int(g): j for j, g in enumerate(kept_slabs)}
+    plan = []
+    for a in range(0, n_surfaces, width):
+        b = min(n_surfaces, a + width)
+        lo, hi = 2 * a, 2 * b
+        local = [(g - lo, position[g]) for g in range(lo if a == 0 else lo + 1, hi + 1) if g in position]
+        chain = b < n_surfaces
+        if chain and (not local or local[-1][0] != hi - lo):
+            local.append((hi - lo, -1))
+        red = None
+        if reduce_slab is not None and ((a == 0 and reduce_slab == 0) or lo < reduce_slab <= hi):
+            red = reduce_slab - lo
+        plan.append((a, b, local, chain, red))
+    return plan
+
+
+def reduce_for_segment(reduce, local_slab):
+    """a copy of an RtbReduce whose slab index is relative to one segment"""
+    one = _ffi.RtbReduce()
+    C.memmove(C.byref(one), C.byref(reduce), C.sizeof(one))
+    one.slab = int(local_slab)
+    return one
+
+
+def _trace_host_long(surfaces, materials, rays, keep, precision, device, reduce, out):
+    S = len(surfaces)
+    if len(materials) != S + 1:
+        raise ValueError("length of materials should be len(surfaces) + 1")
+    n_slabs = 2 * S + 1
+    kept, n_out = global_keep_list(keep, n_slabs)
+    n = rays.shape[0]
+    if out is None:
+        out = _ffi.result_array((n_out, n, 8))
+    elif out.shape != (n_out, n, 8) or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError(f"out must be a C-contiguous float64 array of shape {(n_out, n, 8)}")
+    red_slab = None
+    if reduce is not None:
+        red_slab = int(reduce.slab) + (n_slabs if reduce.slab < 0 else 0)
+    cur = rays
+    for a, b, local, chain, red in plan_segments(S, kept, red_slab):
+        if not local and red is None:
+            continue
+        part = trace_host(surfaces[a:b], materials[a:b + 1], cur, keep=[l for l, _ in local] or "none",
+                          precision=precision, device=device,
+                          reduce=None if red is None else reduce_for_segment(reduce, red))
+        for j, (_, pos) in enumerate(local):
+            if pos >= 0:
+                out[pos] = part[j]
+        if chain:
+            cur = part[len(local) - 1]
+    return out
+
+
 def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64", device: int = 0,
                reduce=None, out: np.ndarray | None = None) -> np.ndarray:
     """
@@ -251,6 +333,8 @@ def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64
     if rays.ndim != 2 or rays.shape[1] != 8:
         raise ValueError(f"rays must have shape (N, 8), got {rays.shape}")
     n = rays.shape[0]
+    if len(surfaces) > _ffi.RTB_MAX_SURFACES:
+        return _trace_host_long(surfaces, materials, rays, keep, precision, device, reduce, out)
     uniq = choose_wavelength_table(materials, rays)
     if uniq is None and any(pack_material(m).kind == KIND_TABLE_ONLY for m in materials):
         return _trace_host_grouped(surfaces, materials, rays, keep, precision, device, reduce, out)

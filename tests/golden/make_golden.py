@@ -3,7 +3,8 @@ Generate the golden vectors for the hot path from the REFERENCE ITSELF.
 
 Run in the build container only (it needs /root/reference, which does not exist on the GPU box):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                      (everything)
+    python tests/golden/make_golden.py --only-big NAME ...  (add / refresh single big-batch checksum pins)
 
 What it writes (all committed):
   tests/golden/<case>.npz      rays_in (N,8), history (2S+1,N,8) from reference System.ray_trace, the system's
@@ -48,7 +49,7 @@ def import_reference():
     return rt, rtm
 
 
-def main():
+def main(only_big=()):
     rt, rtm = import_reference()
     import systems
     import parity
@@ -58,7 +59,7 @@ def main():
     summary = {}
 
     # ------------------------------------------------------------------ per-case golden files
-    for name, builder in systems.CASES.items():
+    for name, builder in ({} if only_big else systems.CASES).items():
         system, m_in, m_out, rays = builder(rt, rtm)
         with np.errstate(all="ignore"):
             hist = system.ray_trace(rays, m_in, m_out)
@@ -99,7 +100,14 @@ def main():
                                  systems.lattice_rays(256, 26.0, -5.0, 0.5)),
         "opm_lattice": (systems.opm_system(rt, rtm)[0], rtm.Constant(1.4), rtm.Vacuum(),
                         systems.lattice_rays(256, 1e-3, 1e-3, 532e-6, tilt=(0.0, 0.0), converge=600.0)),
+        # 70 surfaces: longer than one kernel launch carries (the product chains two segments)
+        "long_train_lattice": (systems.long_train_system(rt, rtm), rtm.Vacuum(), rtm.Vacuum(),
+                               systems.lattice_rays(64, 15.5, 0.0, 0.5876, tilt=(0.002, -0.001))),
     }
+    if only_big:
+        # add / refresh single big-batch pins without rewriting the other (unchanged) golden files
+        merged = json.loads((HERE / "checksums.json").read_text())
+        big = {k: v for k, v in big.items() if k in only_big}
     for name, (system, m_in, m_out, rays) in big.items():
         with np.errstate(all="ignore"):
             hist = system.ray_trace(rays, m_in, m_out)
@@ -110,6 +118,11 @@ def main():
                         "nan_rays_at_end": int(np.isnan(hist[-1, :, 0]).sum()),
                         "system": systems.describe_system(system, m_in, m_out)}
         print(f"{name:22s} N={rays.shape[0]:6d} NaN at end={checks[name]['nan_rays_at_end']:6d}  oracle == reference")
+    if only_big:
+        merged["big"].update(checks)
+        (HERE / "checksums.json").write_text(json.dumps(merged, indent=1))
+        print("updated", sorted(checks), "in", HERE / "checksums.json")
+        return
 
     # ------------------------------------------------------------------ random systems (checksums only)
     rand = {}
@@ -218,4 +231,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # python tests/golden/make_golden.py [--only-big NAME ...]
+    main(tuple(sys.argv[2:]) if len(sys.argv) > 2 and sys.argv[1] == "--only-big" else ())

@@ -185,6 +185,34 @@ def relay10_system(rt, rtm, offset=5.0):
     return system
 
 
+def long_train_system(rt, rtm):
+    """
+    70 surfaces -- more than one kernel launch carries (RTB_MAX_SURFACES = 64), so the product traces it in two chained
+    segments; the reference's loop has no such limit.  33 weak singlets of alternating sign (66 spherical surfaces,
+    three glasses), a window whose back face is tilted, a perfect lens and a screen in its back focal plane.
+    """
+    S = rt.SphericalSurface
+    glasses = [rtm.Bk7(), rtm.Sf10(), rtm.FusedSilica()]
+    surfaces, mats = [], []
+    z = 10.0
+    for k in range(33):
+        sign = 1.0 if k % 2 == 0 else -1.0
+        R = 400.0 + 10.0 * k
+        surfaces.append(S.get_on_axis(sign * R, z, 15.0))
+        mats.append(glasses[k % 3])
+        surfaces.append(S.get_on_axis(-sign * R, z + 3.0, 15.0))
+        mats.append(rtm.Constant(1) if k % 4 else rtm.Vacuum())
+        z += 8.0
+    surfaces.append(rt.FlatSurface([0, 0, z + 5.0], [0, 0, 1], 15.0))
+    mats.append(rtm.Bk7())
+    surfaces.append(rt.FlatSurface([0, 0, z + 8.0], [np.sin(0.05), 0, np.cos(0.05)], 15.0))
+    mats.append(rtm.Vacuum())
+    surfaces.append(rt.PerfectLens(50.0, [0, 0, z + 30.0], [0, 0, 1], 0.25))
+    mats.append(rtm.Vacuum())
+    surfaces.append(rt.FlatSurface([0, 0, z + 80.0], [0, 0, 1], 15.0))
+    return rt.System(surfaces, mats)
+
+
 def relay10(rt, rtm, n_disps=15, nphis=12, n_fields=3, beam_rad=12.0):
     """config 3: tilted collimated bundles through the relay (field angles 0..1 degree)"""
     system = relay10_system(rt, rtm)

@@ -516,6 +516,51 @@ def test_fused_reductions(rt, rtm, oracle, dev, torch):
     assert red.stats_t.cpu().numpy()[0] == 0 and float(red.grid.abs().sum()) == 0.0
 
 
+def test_system_longer_than_one_launch(rt, rtm, oracle, dev, torch):
+    """70 surfaces (> RTB_MAX_SURFACES): two chained segments must give the reference loop's history, in every mode.
+    (The full history and keep="last" are also pinned by the sha256 of the reference's output: long_train_lattice.)"""
+    system = systems.long_train_system(rt, rtm)
+    m_in = m_out = rtm.Vacuum()
+    mats = [m_in] + system.materials + [m_out]
+    rays = systems.lattice_rays(40, 15.5, 0.0, 0.5876, tilt=(0.002, -0.001))
+    rays[::7, 7] = 0.4861                                   # a second wavelength
+    hist = oracle.trace(system.surfaces, mats, rays, keep_all=True, n_threads=8)
+    n_slabs = 2 * 70 + 1
+    assert hist.shape[0] == n_slabs
+    dead_at = np.array([np.isnan(hist[j, :, 0]).sum() for j in (0, 128, 140)])
+    assert dead_at[0] == 0 and dead_at[1] < dead_at[2] < rays.shape[0], dead_at   # rays also die in the second segment
+    parity.assert_bit_identical(system.ray_trace(rays, m_in, m_out), hist, "drop-in call, full history")
+    for keep in ([0, 5, 127, 128, 129, 140], [128], [129, 130], [3], "last", [0]):
+        got = system.ray_trace(rays, m_in, m_out, keep=keep)
+        want = hist[[-1]] if keep == "last" else hist[keep]
+        parity.assert_bit_identical(got, want, f"long system, keep={keep}")
+    # device tensors, both layouts; the fused source path falls back to generate + chain
+    d_rays = torch.from_numpy(rays).cuda()
+    got = dev.trace_tensor(system.surfaces, mats, d_rays, keep=[1, 128, 139, 140])
+    parity.assert_bit_identical(got.cpu().numpy(), hist[[1, 128, 139, 140]], "long system, tensor API")
+    got = dev.trace_tensor(system.surfaces, mats, d_rays.t().contiguous(), keep=[64, 130], layout="planes")
+    parity.assert_bit_identical(got.permute(0, 2, 1).contiguous().cpu().numpy(), hist[[64, 130]], "long system, planes")
+    src = dev.RaySource.grid([0, 0, 0.0], 12.0, 33, 0.5876)
+    s_rays = src.generate().cpu().numpy()
+    s_hist = oracle.trace(system.surfaces, mats, s_rays, keep_all=True, n_threads=8)
+    got = dev.trace_source(system.surfaces, mats, src, keep=[100, 140])
+    parity.assert_bit_identical(got.cpu().numpy(), s_hist[[100, 140]], "long system, fused source")
+    # fused reductions at a slab of the first and of the second segment (negative index included)
+    for slab in (100, 130, -1):
+        red = dev.Reducer(slab, origin=(0, 0, 0), grid_n=32, half_width=16.0)
+        out = dev.trace_tensor(system.surfaces, mats, d_rays, keep="last", reducer=red)
+        parity.assert_bit_identical(out[0].cpu().numpy(), hist[-1], "long system, keep last + reduction")
+        want = oracle.reduce_stats(hist[slab], (0, 0, 0), (1, 0, 0), (0, 1, 0))
+        got_stats = red.stats_t.cpu().numpy()
+        assert got_stats[0] == want[0] > 100
+        np.testing.assert_allclose(got_stats[1:8], want[1:8], rtol=1e-10, atol=1e-6)
+        assert np.array_equal(red.grid.cpu().numpy()[2],
+                              oracle.reduce_grid(hist[slab], (0, 0, 0), (1, 0, 0), (0, 1, 0), 32, 16.0)[2])
+    # structural errors are the reference's
+    with pytest.raises(ValueError):
+        system.ray_trace(rays, m_in, m_out, keep=[141])
+
+
 def test_reduction_at_input_and_with_source(rt, rtm, oracle, dev):
     system, m_in, m_out, _ = systems.plano_convex(rt, rtm)
     mats = [m_in] + system.materials + [m_out]

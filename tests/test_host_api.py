@@ -304,3 +304,34 @@ def test_raytrace_shim_package(rt):
     import raytrace.raytrace as shim
     assert shim.System is rt.System and shim.get_ray_fan is rt.get_ray_fan
     assert shim_m.Nsf11 is not None
+
+
+def test_plan_segments_covers_every_slab_once():
+    """systems longer than one launch: the segment plan returns each requested slab exactly once, in order, and
+    chains through the last slab of every segment but the final one"""
+    from ray_trace_pb_b200 import engine
+    for S, width in ((70, 64), (130, 64), (64, 64), (5, 2), (1, 64)):
+        n_slabs = 2 * S + 1
+        for kept in (list(range(n_slabs)), [n_slabs - 1], [], [0], [2 * min(S, width)], [1, 2 * min(S, width) + 1],
+                     list(range(0, n_slabs, 3))):
+            kept = sorted({k for k in kept if k < n_slabs})
+            plan = engine.plan_segments(S, kept, reduce_slab=None, width=width)
+            assert [a for a, *_ in plan] == list(range(0, S, width))
+            seen = []
+            for a, b, local, chain, red in plan:
+                assert b - a <= width and chain == (b < S) and red is None
+                slabs = [l for l, _ in local]
+                assert slabs == sorted(set(slabs)) and all(0 <= l <= 2 * (b - a) for l in slabs)
+                if chain:
+                    assert slabs[-1] == 2 * (b - a)
+                seen += [(2 * a + l, pos) for l, pos in local if pos >= 0]
+            assert [g for g, _ in seen] == kept and [p for _, p in seen] == list(range(len(kept)))
+        # a reduction lands in exactly one segment, at the right local slab
+        for g in (0, 1, 2 * min(S, width), min(2 * min(S, width) + 1, n_slabs - 1), n_slabs - 1):
+            hits = [(a, red) for a, b, local, chain, red in engine.plan_segments(S, [], g, width) if red is not None]
+            assert len(hits) == 1 and 2 * hits[0][0] + hits[0][1] == g
+    kept, n_out = engine.global_keep_list("last", 141)
+    assert kept == [140] and n_out == 1
+    assert engine.global_keep_list("all", 5) == ([0, 1, 2, 3, 4], 5)
+    assert engine.global_keep_list([-1, ], 141)[0] == [140]
+

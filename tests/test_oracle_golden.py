@@ -45,6 +45,7 @@ BIG = {
     "relay10_lattice_wide": lambda: systems.lattice_rays(200, 27.0, 0.0, 0.785, tilt=(0.0, 0.0), converge=1e-4),
     "plano_convex_lattice": lambda: systems.lattice_rays(256, 26.0, -5.0, 0.5),
     "opm_lattice": lambda: systems.lattice_rays(256, 1e-3, 1e-3, 532e-6, tilt=(0.0, 0.0), converge=600.0),
+    "long_train_lattice": lambda: systems.lattice_rays(64, 15.5, 0.0, 0.5876, tilt=(0.002, -0.001)),
 }
 
 
