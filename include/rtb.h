@@ -69,9 +69,19 @@ typedef enum rtb_material_kind {
  * the axis used by the "ray comes from the front" cull and the sphere's aperture test (raytrace.py:1189, 1531).
  * System.reverse() flips only the latter (raytrace.py:409-411), so both are carried.
  */
+/*
+ * rtb_surface.hints (optional, 0 = none).  Hints never change a result -- every route computes the same bits -- only
+ * which code path gets there first.
+ * RTB_HINT_DEGENERATE  on a flat refracting surface: the bundle meets it with exact zeros ray after ray (the rays
+ *                      start on the plane, t = +-0, or run exactly along its normal, d x n = 0 -- what the reference's
+ *                      scripts do with their first surface).  The hot loop then handles those zeros in line instead of
+ *                      redoing every ray out of line.  Costs a few percent at that surface when the bundle is ordinary.
+ */
+#define RTB_HINT_DEGENERATE 1
+
 typedef struct rtb_surface {
     int32_t kind; /* rtb_surface_kind */
-    int32_t reserved;
+    int32_t hints; /* RTB_HINT_* */
     double center[3];
     double normal[3];
     double input_axis[3];

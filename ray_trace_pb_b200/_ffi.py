@@ -34,6 +34,7 @@ MAT_CONSTANT, MAT_SELLMEIER, MAT_TABLE_ONLY = 0, 1, 2
 F64_EXACT, F32_FAST, F64_FAST = 0, 1, 2
 KEEP_ALL, KEEP_LAST, KEEP_LIST, KEEP_NONE = 0, 1, 2, 3
 SRC_COLLIMATED, SRC_FAN, SRC_GRID = 0, 1, 2
+HINT_DEGENERATE = 1          # rtb_surface.hints
 FLAG_INTERSECT_ONLY = 1
 FLAG_PLANES_IN = 2
 FLAG_PLANES_OUT = 4
@@ -42,7 +43,7 @@ _d3 = C.c_double * 3
 
 
 class RtbSurface(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("kind", C.c_int32), ("hints", C.c_int32),
                 ("center", _d3), ("normal", _d3), ("input_axis", _d3),
                 ("radius", C.c_double), ("radius_sq", C.c_double), ("abs_radius", C.c_double),
                 ("aperture_rad", C.c_double), ("focal_len", C.c_double), ("normal_f", _d3),

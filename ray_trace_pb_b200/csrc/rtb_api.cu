@@ -214,6 +214,7 @@ int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TracePar
         };
         d.z_normal = z_aligned(a.normal);
         d.z_axis = z_aligned(a.input_axis);
+        d.degenerate_hint = (a.hints & RTB_HINT_DEGENERATE) ? 1 : 0;
         d.ap_sq_max = sq_upper(a.aperture_rad);
         double lo, hi;
         on_sphere_window(a.abs_radius, 1e-12, lo, hi);

@@ -50,7 +50,8 @@ struct DevSurface {
     int32_t kind;
     int8_t z_normal; // +-1 when normal == (0, 0, +-1) exactly, else 0   (shortcuts of the Optimistic policy)
     int8_t z_axis;   // +-1 when input_axis == (0, 0, +-1) exactly, else 0
-    int16_t pad;
+    int8_t degenerate_hint; // rtb_surface.hints & RTB_HINT_DEGENERATE (flat surfaces: zero forms in the hot loop)
+    int8_t pad;
 };
 
 struct DevMaterial {

@@ -20,6 +20,7 @@
 //     ("Careful") instantiation when the flag fails; terms multiplied by the exact zeros of a z-aligned normal or
 //     axis are dropped when all operands are known finite (surface_steps.cuh).
 #include <cmath>
+#include <type_traits>
 #include <math_constants.h>
 
 #include "exact_math.cuh"
@@ -37,15 +38,75 @@ struct SharedConsts {
     unsigned long long rcp_ok;       // bit k: that reciprocal is usable by the Optimistic steps (see below)
 };
 
+// The final-slab-only kernel's surface step as a FUNCTION: it must be inlined at both of its call sites -- out of line,
+// the prescription would be read through generic pointers into the parameter block, at half the speed -- and only
+// functions can be forced (the general kernel's lambda below is inlined by the compiler's own choice, and that
+// kernel's register allocation does not take kindly to being rearranged).
+struct RayLoop {       // the loop-carried state of one ray
+    Ray cur;
+    double n1, n2;     // refractive index before / after the current surface
+    double wl0;        // launch wavelength
+    xm::Rcp rcp_wl;
+    int row;           // this ray's row of the index tables (times the number of media)
+    bool unlisted;     // valid wavelength that the host table does not list
+    bool dead;
+    bool force_careful;
+};
+
+template <class OPT, bool USE_TABLE>
+__device__ __forceinline__ void plain_surface_step(const TraceParams &P, const double *s_ntab, const double *s_ratio,
+                                                   const SharedConsts &s_c, int kk, RayLoop &st)
+{
+    const DevSurface &s = P.surf[kk];
+    st.n2 = !USE_TABLE ? eval_index(P.mat[kk + 1], st.wl0)
+                       : (st.unlisted ? index_for_unlisted(&P.mat[kk + 1], st.wl0) : s_ntab[st.row + kk + 1]);
+    xm::Rcp rcp_k;
+    rcp_k.b = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
+    rcp_k.y = s_c.rcp_radius[kk];
+    rcp_k.ok = (s_c.rcp_ok >> kk) & 1ull;
+    OPT m;
+    m.ok = !st.force_careful;
+    st.force_careful = false;
+    AtRaw raw;
+    Ray after;
+    if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE) {
+        const double ratio = (USE_TABLE && !st.unlisted) ? s_ratio[st.row + kk] : xm::div(st.n1, st.n2);
+        st.dead = refracting_step<OPT, false>(m, s, st.cur, st.n1, ratio, st.rcp_wl, rcp_k, true, raw, after);
+        if (!m.ok) {
+            const StepResult redo = careful_refracting(&s, st.cur, st.n1, ratio, true);
+            after = redo.after;
+            st.dead = redo.dead;
+        }
+    } else if (s.kind == RTB_SURF_MIRROR) {
+        st.dead = mirror_step<OPT, false>(m, s, st.cur, st.n1, st.rcp_wl, raw, after);
+        if (!m.ok) {
+            const StepResult redo = careful_mirror(&s, st.cur, st.n1);
+            after = redo.after;
+            st.dead = redo.dead;
+        }
+    } else {
+        st.dead = perfect_lens_step<OPT>(m, s, st.cur, st.n1, st.n2, st.rcp_wl, rcp_k, false, false, raw, after);
+        if (!m.ok) {
+            const StepResult redo = careful_lens(&s, st.cur, st.n1, st.n2, false);
+            after = redo.after;
+            st.dead = redo.dead;
+        }
+    }
+    st.cur = after;
+    st.n1 = st.n2;
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------
 // USE_TABLE   refractive indices (and n1/n2) from the host table (any material), else in-register Sellmeier.
 // FROM_SOURCE rays are produced by the on-device source instead of being read from memory.
 // MODE        0: only the final slab is stored; 1: general (any slab selection, fused reductions); 2: general, as a
 //             sweep over P.n_src sources (FROM_SOURCE only): blockIdx.y picks the source, its output rows and its
 //             reduction bucket.
-template <bool USE_TABLE, bool FROM_SOURCE, int MODE>
+// HINTED      the launch carries surface hints (rtb_surface.hints): the hot loop runs on OptimisticFlatZ.
+template <bool USE_TABLE, bool FROM_SOURCE, int MODE, bool HINTED>
 __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kernel(const __grid_constant__ TraceParams P)
 {
+    using Optimistic = std::conditional_t<HINTED, OptimisticFlatZ, rtb::Optimistic>;
     constexpr bool GENERAL = MODE >= 1;
     constexpr bool SWEEP = MODE == 2;
     static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
@@ -239,14 +300,22 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             // two surfaces per trip: the ray's registers ping-pong between the two copies of the body instead of
             // being moved back at the end of every surface (+3 % here; the general mode's loop loses by it)
 #pragma unroll 1
-            for (; k + 1 < P.n_surf && !dead; k += 2) {
-                plain_surface(k);
-                if (!dead) plain_surface(k + 1);
+            RayLoop st;
+            st.cur = cur;
+            st.n1 = n1;
+            st.n2 = n2;
+            st.wl0 = wl0;
+            st.rcp_wl = rcp_wl;
+            st.row = row;
+            st.unlisted = unlisted;
+            st.dead = false;
+            st.force_careful = force_careful;
+            for (; k < P.n_surf && !st.dead; k += 2) {
+                plain_surface_step<Optimistic, USE_TABLE>(P, s_ntab, s_ratio, s_c, k, st);
+                if (k + 1 < P.n_surf && !st.dead) plain_surface_step<Optimistic, USE_TABLE>(P, s_ntab, s_ratio, s_c, k + 1, st);
             }
-            if (k < P.n_surf && !dead) {
-                plain_surface(k);
-                k++;
-            }
+            cur = st.cur;
+            dead = st.dead;
         } else {
             // runs of surfaces whose "at" slab is not needed go through the same tight loop as the final-slab-only kernel
             while (k < P.n_surf && !dead) {
@@ -287,7 +356,13 @@ template <bool T, bool S, int M>
 cudaError_t launch_one(const TraceParams &P, unsigned blocks, cudaStream_t stream)
 {
     const size_t tables = T ? 2 * sizeof(double) * (size_t)(P.n_wl + 1) * (size_t)(P.n_surf + 1) : 0;
-    trace_f64_kernel<T, S, M><<<dim3(blocks, M == 2 ? (unsigned)P.n_src : 1u), kTraceThreads, tables, stream>>>(P);
+    const dim3 grid(blocks, M == 2 ? (unsigned)P.n_src : 1u);
+    bool hinted = false;
+    for (int k = 0; k < P.n_surf; k++) hinted |= P.surf[k].degenerate_hint != 0;
+    if (hinted)
+        trace_f64_kernel<T, S, M, true><<<grid, kTraceThreads, tables, stream>>>(P);
+    else
+        trace_f64_kernel<T, S, M, false><<<grid, kTraceThreads, tables, stream>>>(P);
     return cudaGetLastError();
 }
 

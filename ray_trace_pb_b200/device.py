@@ -73,7 +73,7 @@ def _system_for(surfaces, materials, wavelengths):
 
 
 def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelengths="auto", reducer=None,
-                 out=None, flags: int = 0, layout: str = "rows"):
+                 out=None, flags: int = 0, layout: str = "rows", degenerate_first=None):
     """
     rays: (N, 8) float64 CUDA tensor; ``materials`` = [initial] + system.materials + [final].
     wavelengths: "auto" scans the batch on the device for its distinct wavelengths (one extra pass over column 7);
@@ -81,6 +81,9 @@ def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelen
     layout: "rows" = the reference's (N, 8) in, (n_slabs, N, 8) out; "planes" = structure-of-arrays, (8, N) in and
     (n_slabs, 8, N) out (one contiguous plane per column; give ``wavelengths`` explicitly or it is scanned from a
     row-major copy of the wavelength plane).
+    degenerate_first: True / False = the bundle does / does not meet a flat first surface with exact zeros ray after
+    ray (engine.degenerate_first_surface; a speed hint only), "auto" = decide from a 64-ray sample copied to the host
+    (one small synchronising read), None = no hint.
     Returns a CUDA tensor on the same device (None for keep="none").  Enqueued on the current stream.
     """
     torch = _torch()
@@ -98,9 +101,20 @@ def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelen
             wavelengths = distinct_wavelengths_tensor(probe)
         else:
             wavelengths = distinct_wavelengths_tensor(rays)
+    if isinstance(degenerate_first, str):
+        if degenerate_first != "auto":
+            raise ValueError("degenerate_first must be True, False, None or 'auto'")
+        n_all = rays.shape[1] if planes else rays.shape[0]
+        degenerate_first = False
+        if n_all:
+            pick = torch.linspace(0, n_all - 1, min(n_all, 64), device=rays.device).long()
+            sample = (rays[:, pick].t() if planes else rays[pick]).cpu().numpy()
+            degenerate_first = engine.degenerate_first_surface(surfaces, rays=sample)
     if len(surfaces) > _ffi.RTB_MAX_SURFACES:
-        return _trace_tensor_long(surfaces, materials, rays, keep, precision, wavelengths, reducer, out, flags, layout)
+        return _trace_tensor_long(surfaces, materials, rays, keep, precision, wavelengths, reducer, out, flags, layout,
+                                  degenerate_first)
     packed = _system_for(surfaces, materials, wavelengths)
+    engine.set_first_surface_hint(packed, bool(degenerate_first))
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
     opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
     opts.flags = flags | ((_ffi.FLAG_PLANES_IN | _ffi.FLAG_PLANES_OUT) if planes else 0)
@@ -125,7 +139,8 @@ class _SegmentReducer:
         self.struct = engine.reduce_for_segment(reducer.struct, local_slab)
 
 
-def _trace_tensor_long(surfaces, materials, rays, keep, precision, wavelengths, reducer, out, flags, layout):
+def _trace_tensor_long(surfaces, materials, rays, keep, precision, wavelengths, reducer, out, flags, layout,
+                       degenerate_first=None):
     """A system of more than RTB_MAX_SURFACES surfaces, in segments chained on the device (engine.plan_segments)."""
     torch = _torch()
     planes = layout == "planes"
@@ -151,7 +166,8 @@ def _trace_tensor_long(surfaces, materials, rays, keep, precision, wavelengths, 
             continue
         part = trace_tensor(surfaces[a:b], materials[a:b + 1], cur, keep=[l for l, _ in local] or "none",
                             precision=precision, wavelengths=wavelengths,
-                            reducer=None if red is None else _SegmentReducer(reducer, red), flags=flags, layout=layout)
+                            reducer=None if red is None else _SegmentReducer(reducer, red), flags=flags, layout=layout,
+                            degenerate_first=degenerate_first if a == 0 else None)
         for j, (_, pos) in enumerate(local):
             if pos >= 0:
                 out[pos].copy_(part[j])
@@ -185,6 +201,13 @@ class RaySource:
     @property
     def n_rays(self) -> int:
         return self.n_a * self.n_b
+
+    def degenerate_at_first(self, surfaces) -> bool:
+        """engine.degenerate_first_surface for this source: a fan's rays share their origin, the rays of a collimated
+        bundle or grid their direction (and lie in the plane through ``pt`` across it)."""
+        if self.kind == _ffi.SRC_FAN:
+            return engine.degenerate_first_surface(surfaces, origin=self.pt)
+        return engine.degenerate_first_surface(surfaces, direction=self.axis)
 
     @classmethod
     def fan(cls, pt, theta_max, n_thetas, wavelength, nphis=1, center_ray=(0, 0, 1)):
@@ -267,9 +290,10 @@ def trace_source(surfaces, materials, source: RaySource, first: int = 0, count: 
         rays = source.generate(first, count, device=device)
         return trace_tensor(surfaces, materials, rays, keep=keep, precision=precision,
                             wavelengths=[source.wavelength] if np.isfinite(source.wavelength) else None,
-                            reducer=reducer, out=out)
+                            reducer=reducer, out=out, degenerate_first=source.degenerate_at_first(surfaces))
     if packed is None:
         packed = _system_for(surfaces, materials, [source.wavelength] if np.isfinite(source.wavelength) else None)
+    engine.set_first_surface_hint(packed, source.degenerate_at_first(surfaces))
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
     opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
     if n_out == 0:
@@ -307,6 +331,7 @@ def trace_sources(surfaces, materials, sources, first: int = 0, count: int | Non
     if packed is None:
         wls = sorted({float(s.wavelength) for s in sources if np.isfinite(s.wavelength)})
         packed = _system_for(surfaces, materials, wls or None)
+    engine.set_first_surface_hint(packed, all(s.degenerate_at_first(surfaces) for s in sources))
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
     opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
     if n_out == 0:

@@ -62,6 +62,60 @@ def pack_surface(s) -> _ffi.RtbSurface:
     return out
 
 
+# ----------------------------------------------------------------------------------------------------------
+# hints (rtb_surface.hints): never change a result, only which code path reaches it first
+# ----------------------------------------------------------------------------------------------------------
+def _first_flat(surfaces):
+    from . import raytrace as _rt
+    if not surfaces or not isinstance(surfaces[0], _rt.FlatSurface):
+        return None
+    s = surfaces[0]
+    return np.asarray(s.center, dtype=np.float64).reshape(3), np.asarray(s.normal, dtype=np.float64).reshape(3)
+
+
+def degenerate_first_surface(surfaces, rays=None, origin=None, direction=None) -> bool:
+    """
+    Does the bundle meet a FLAT first surface with exact zeros, ray after ray -- starting on the plane (t = +-0) or
+    running exactly along its normal (d x n = 0)?  That is how the reference's scripts launch their rays (a flat at
+    z = 0 under a collimated beam or a point source), and the kernel handles it in line when told
+    (RTB_HINT_DEGENERATE) instead of redoing every ray out of line.
+
+    ``rays``: a host sample of the batch, (n, 8); or ``origin`` / ``direction``: the point / direction every ray of an
+    on-device source shares (either may be None).  A wrong answer only costs speed.
+    """
+    flat = _first_flat(surfaces)
+    if flat is None:
+        return False
+    c, n = flat
+    with np.errstate(all="ignore"):
+        if rays is not None:
+            r = np.asarray(rays, dtype=np.float64).reshape(-1, 8)
+            r = r[np.isfinite(r[:, :6]).all(axis=1)]
+            if r.shape[0] == 0:
+                return False
+            num = ((r[:, 0] - c[0]) * n[0] + (r[:, 1] - c[1]) * n[1]) + (r[:, 2] - c[2]) * n[2]
+            d = r[:, 3:6]
+            cross = np.stack((d[:, 1] * n[2] - d[:, 2] * n[1], d[:, 2] * n[0] - d[:, 0] * n[2],
+                              d[:, 0] * n[1] - d[:, 1] * n[0]), axis=1)
+            return bool((num == 0).all() or (cross == 0).all())
+        on_plane = along = False
+        if origin is not None:
+            o = np.asarray(origin, dtype=np.float64).reshape(3)
+            on_plane = bool(((o[0] - c[0]) * n[0] + (o[1] - c[1]) * n[1]) + (o[2] - c[2]) * n[2] == 0)
+        if direction is not None:
+            d = np.asarray(direction, dtype=np.float64).reshape(3)
+            along = bool(d[1] * n[2] - d[2] * n[1] == 0 and d[2] * n[0] - d[0] * n[2] == 0
+                         and d[0] * n[1] - d[1] * n[0] == 0)
+        return on_plane or along
+
+
+def set_first_surface_hint(packed, degenerate: bool):
+    """mark / unmark surface 0 of a packed system (a PackedSystem is reused across launches by device.prepare)"""
+    if packed.n_surfaces > 0:
+        packed.sys.surfaces[0].hints = _ffi.HINT_DEGENERATE if degenerate else 0
+    return packed
+
+
 def pack_material(m) -> _ffi.RtbMaterial:
     rec = getattr(m, "device_record", None)
     out = _ffi.RtbMaterial()
@@ -339,6 +393,9 @@ def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64
     if uniq is None and any(pack_material(m).kind == KIND_TABLE_ONLY for m in materials):
         return _trace_host_grouped(surfaces, materials, rays, keep, precision, device, reduce, out)
     packed = pack_system(surfaces, materials, uniq)
+    if n:
+        sample = rays[np.linspace(0, n - 1, num=min(n, 64)).astype(np.int64)]
+        set_first_surface_hint(packed, degenerate_first_surface(surfaces, rays=sample))
     mode, idx, n_out = resolve_keep(keep, packed.n_slabs)
     opts = make_opts(mode, idx, precision, reduce)
     if out is None:

@@ -12,7 +12,7 @@ L = C.CDLL(str(Path(__file__).resolve().parent.parent / "ray_trace_pb_b200" / "_
 
 
 class RtbSurface(C.Structure):       # include/rtb.h: rtb_surface
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("center", C.c_double * 3), ("normal", C.c_double * 3),
+    _fields_ = [("kind", C.c_int32), ("hints", C.c_int32), ("center", C.c_double * 3), ("normal", C.c_double * 3),
                 ("input_axis", C.c_double * 3), ("radius", C.c_double), ("radius_sq", C.c_double),
                 ("abs_radius", C.c_double), ("aperture_rad", C.c_double), ("focal_len", C.c_double),
                 ("normal_f", C.c_double * 3), ("sin_alpha", C.c_double)]

@@ -155,6 +155,46 @@ def test_degenerate_bundles_stay_on_the_fast_path_and_match(rt, rtm, oracle, tor
     assert np.isfinite(want[-1]).all()
 
 
+def test_degenerate_first_surface_hint_never_changes_a_result(rt, rtm, oracle, torch, dev):
+    """RTB_HINT_DEGENERATE selects the kernels whose hot loop handles exact zeros at a marked flat in line: the same
+    bits with the hint on or off, on bundles that are degenerate there, on bundles that are not, and on mixtures."""
+    from ray_trace_pb_b200 import engine
+    system, m_in, m_out = systems.rebuild_system(load_golden("doublet_nlak22")["system"], rt, rtm)
+    mats = [m_in] + system.materials + [m_out]
+    assert isinstance(system.surfaces[0], rt.FlatSurface)
+    z0 = float(system.surfaces[0].center[2])
+    on_plane = systems.lattice_rays(120, 9.0, z0, 0.855, tilt=(0.01, -0.02))            # t = +-0 at the first flat
+    along = systems.lattice_rays(120, 9.0, z0 - 7.0, 0.855)                             # d x n = 0 there
+    ordinary = systems.lattice_rays(120, 9.0, z0 - 7.0, 0.855, tilt=(0.01, -0.02))
+    mixed = np.concatenate((on_plane[::3], along[1::3], ordinary[2::3]))
+    mixed[5, 0] = np.inf
+    for name, rays, expect in (("on plane", on_plane, True), ("along normal", along, True),
+                               ("ordinary", ordinary, False), ("mixed", mixed, False)):
+        assert engine.degenerate_first_surface(system.surfaces, rays=rays[::97]) == expect, name
+        want = oracle.trace(system.surfaces, mats, rays, keep_all=True, n_threads=8)
+        d_rays = torch.from_numpy(rays).cuda()
+        for hint in (None, False, True, "auto"):
+            for keep in ("all", "last"):
+                got = dev.trace_tensor(system.surfaces, mats, d_rays, keep=keep, degenerate_first=hint)
+                parity.assert_bit_identical(got.cpu().numpy(), want if keep == "all" else want[[-1]],
+                                            f"{name}, hint={hint}, keep={keep}")
+        parity.assert_bit_identical(system.ray_trace(rays, m_in, m_out), want, f"{name}, drop-in call (sampled hint)")
+    # on-device sources decide from their own description
+    src = dev.RaySource.grid([0, 0, z0], 8.0, 201, 0.855)
+    assert src.degenerate_at_first(system.surfaces)
+    assert not dev.RaySource.grid([0, 0, z0 - 1.0], 8.0, 201, 0.855, normal=(0, np.sin(0.1), np.cos(0.1))
+                                  ).degenerate_at_first(system.surfaces)
+    fan_on = dev.RaySource.fan([0.5, 0, z0], 0.1, 101, 0.855, nphis=50)
+    assert fan_on.degenerate_at_first(system.surfaces)
+    for source in (src, fan_on):
+        rays = source.generate().cpu().numpy()
+        want = oracle.trace(system.surfaces, mats, rays, keep_all=True, n_threads=8)
+        got = dev.trace_source(system.surfaces, mats, source, keep="all")
+        parity.assert_bit_identical(got.cpu().numpy(), want, "fused source with the hint")
+    with pytest.raises(ValueError):
+        dev.trace_tensor(system.surfaces, mats, d_rays, degenerate_first="maybe")
+
+
 def test_fuzz_opm_vs_oracle(rt, rtm, oracle):
     system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
     rays = rt.get_ray_fan([1e-3, -2e-3, 5e-4], 1.05 * alpha1, 301, 532e-6, nphis=97)

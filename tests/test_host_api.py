@@ -335,3 +335,39 @@ def test_plan_segments_covers_every_slab_once():
     assert engine.global_keep_list("all", 5) == ([0, 1, 2, 3, 4], 5)
     assert engine.global_keep_list([-1, ], 141)[0] == [140]
 
+
+def test_degenerate_first_surface_detection(rt, rtm):
+    """the speed hint for bundles that meet a flat first surface with exact zeros (engine.degenerate_first_surface)"""
+    from ray_trace_pb_b200 import engine
+    flat = rt.FlatSurface([0, 0, 2.0], [0, 0, 1], 10.0)
+    tilted = rt.FlatSurface([0, 0, 2.0], [0, np.sin(0.25), np.cos(0.25)], 10.0)
+    sphere = rt.SphericalSurface.get_on_axis(50.0, 2.0, 10.0)
+    rays = np.zeros((5, 8))
+    rays[:, 0] = np.linspace(-1, 1, 5)
+    rays[:, 5] = 1.0
+    rays[:, 7] = 0.5
+    assert engine.degenerate_first_surface([flat], rays=rays)                     # along the normal
+    assert not engine.degenerate_first_surface([tilted], rays=rays)
+    assert not engine.degenerate_first_surface([sphere], rays=rays)
+    assert not engine.degenerate_first_surface([], rays=rays)
+    skew = rays.copy()
+    skew[:, 3], skew[:, 5] = 0.6, 0.8
+    assert not engine.degenerate_first_surface([flat], rays=skew)
+    skew[:, 2] = 2.0
+    assert engine.degenerate_first_surface([flat], rays=skew)                     # launched on the plane
+    skew[2, 2] = 2.5
+    assert not engine.degenerate_first_surface([flat], rays=skew)                 # ... but not all of them
+    skew[2, :3] = np.nan
+    assert engine.degenerate_first_surface([flat], rays=skew)                     # invalid rows do not vote
+    assert not engine.degenerate_first_surface([flat], rays=np.full((3, 8), np.nan))
+    assert engine.degenerate_first_surface([flat], origin=[3, 4, 2.0]) and not engine.degenerate_first_surface(
+        [flat], origin=[3, 4, 2.1])
+    assert engine.degenerate_first_surface([flat], direction=[0, 0, -1]) and not engine.degenerate_first_surface(
+        [flat], direction=[0, 0.6, 0.8])
+    packed = engine.pack_system([flat, sphere], [rtm.Vacuum(), rtm.Bk7(), rtm.Vacuum()], None)
+    assert packed.sys.surfaces[0].hints == 0
+    engine.set_first_surface_hint(packed, True)
+    assert packed.sys.surfaces[0].hints == 1 and packed.sys.surfaces[1].hints == 0
+    engine.set_first_surface_hint(packed, False)
+    assert packed.sys.surfaces[0].hints == 0
+
