@@ -28,6 +28,10 @@
 #include "surface_steps.cuh"
 #include "trace_common.cuh"
 
+#ifndef RTB_TU_HINTED
+#define RTB_TU_HINTED 0
+#endif
+
 namespace rtb {
 
 namespace {
@@ -357,19 +361,30 @@ cudaError_t launch_one(const TraceParams &P, unsigned blocks, cudaStream_t strea
 {
     const size_t tables = T ? 2 * sizeof(double) * (size_t)(P.n_wl + 1) * (size_t)(P.n_surf + 1) : 0;
     const dim3 grid(blocks, M == 2 ? (unsigned)P.n_src : 1u);
-    bool hinted = false;
-    for (int k = 0; k < P.n_surf; k++) hinted |= P.surf[k].degenerate_hint != 0;
-    if (hinted)
-        trace_f64_kernel<T, S, M, true><<<grid, kTraceThreads, tables, stream>>>(P);
-    else
-        trace_f64_kernel<T, S, M, false><<<grid, kTraceThreads, tables, stream>>>(P);
+    trace_f64_kernel<T, S, M, RTB_TU_HINTED != 0><<<grid, kTraceThreads, tables, stream>>>(P);
     return cudaGetLastError();
 }
 
 } // namespace
 
-// launcher used by rtb_api.cu
+// launchers used by rtb_api.cu.  This file is compiled twice (Makefile): RTB_TU_HINTED = 0 gives the kernels of launches
+// without surface hints (launch_trace_f64 picks), RTB_TU_HINTED = 1 those of hinted launches -- two translation units
+// so that the twenty instantiations build in parallel.
+#if RTB_TU_HINTED
+cudaError_t launch_trace_f64_hinted(const TraceParams &P, int sm_count, cudaStream_t stream)
+#else
+cudaError_t launch_trace_f64_hinted(const TraceParams &P, int sm_count, cudaStream_t stream);
+static cudaError_t launch_trace_f64_plain(const TraceParams &P, int sm_count, cudaStream_t stream);
+
 cudaError_t launch_trace_f64(const TraceParams &P, int sm_count, cudaStream_t stream)
+{
+    bool hinted = false;
+    for (int k = 0; k < P.n_surf; k++) hinted |= P.surf[k].degenerate_hint != 0;
+    return hinted ? launch_trace_f64_hinted(P, sm_count, stream) : launch_trace_f64_plain(P, sm_count, stream);
+}
+
+static cudaError_t launch_trace_f64_plain(const TraceParams &P, int sm_count, cudaStream_t stream)
+#endif
 {
     if (P.n_rays <= 0) return cudaSuccess;
     long long blocks = (P.n_rays + kTraceThreads - 1) / kTraceThreads;
