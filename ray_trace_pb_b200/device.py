@@ -83,7 +83,8 @@ def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelen
     row-major copy of the wavelength plane).
     degenerate_first: True / False = the bundle does / does not meet a flat first surface with exact zeros ray after
     ray (engine.degenerate_first_surface; a speed hint only), "auto" = decide from a 64-ray sample copied to the host
-    (one small synchronising read), None = no hint.
+    (one small synchronising read), None = no hint -- except with wavelengths="auto", which synchronises anyway and
+    therefore also samples for the hint.
     Returns a CUDA tensor on the same device (None for keep="none").  Enqueued on the current stream.
     """
     torch = _torch()
@@ -95,6 +96,8 @@ def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelen
     if isinstance(wavelengths, str):
         if wavelengths != "auto":
             raise ValueError("wavelengths must be 'auto', None or a sequence of values")
+        if degenerate_first is None:
+            degenerate_first = "auto"       # this route reads from the device anyway: the hint's sample rides along
         if planes:
             probe = torch.zeros((rays.shape[1], 8), dtype=torch.float64, device=rays.device)
             probe[:, 7] = rays[7]
