@@ -17,6 +17,7 @@ from oracle import oracle  # noqa: E402  (checker only)
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 bad = 0
+hinted = 0
 alive = []
 for seed in range(first, first + count):
     system, m_in, m_out, rays = systems.random_system(rt, rtm, seed, n_rays=3000)
@@ -28,7 +29,18 @@ for seed in range(first, first + count):
         if not np.array_equal(a, b):
             bad += 1
             print(f"seed {seed} keep={keep}: MISMATCH\n" + parity.mismatch_report(got, ref))
+    if isinstance(system.surfaces[0], rt.FlatSurface):
+        # the kernels of hinted launches (a hint that does not apply is legal: it only costs speed)
+        import torch
+        from ray_trace_pb_b200 import device as dev
+        mats = [m_in] + system.materials + [m_out]
+        got = dev.trace_tensor(system.surfaces, mats, torch.from_numpy(rays).cuda(), keep="all", degenerate_first=True)
+        hinted += 1
+        if not np.array_equal(parity.canonical(got.cpu().numpy()), parity.canonical(want)):
+            bad += 1
+            print(f"seed {seed} hinted: MISMATCH\n" + parity.mismatch_report(got.cpu().numpy(), want))
     alive.append(int(np.isfinite(want[-1, :, 0]).sum()))
-print(f"seeds {first}..{first + count - 1}: {bad} mismatching traces; rays alive at the end: min {min(alive)}, "
+print(f"seeds {first}..{first + count - 1}: {bad} mismatching traces ({hinted} systems start with a flat and were also "
+      f"traced with RTB_HINT_DEGENERATE); rays alive at the end: min {min(alive)}, "
       f"median {int(np.median(alive))}, max {max(alive)} of 3000")
 sys.exit(1 if bad else 0)
