@@ -460,6 +460,8 @@ int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_s
     if (!srcs) return fail(RTB_ERR_INVALID, "source list pointer is NULL");
     if (n_src < 1 || n_src > 65535) return fail(RTB_ERR_INVALID, "n_src = %d, expected 1 .. 65535", n_src);
     if (opts->flags & RTB_FLAG_PLANES_IN) return fail(RTB_ERR_INVALID, "RTB_FLAG_PLANES_IN has no meaning for sources");
+    if (opts->flags & RTB_FLAG_INTERSECT_ONLY)
+        return fail(RTB_ERR_UNSUPPORTED, "RTB_FLAG_INTERSECT_ONLY is not offered for sweeps (one source per call: rtb_trace_source)");
     std::vector<rtb::DevSource> list((size_t)n_src);
     for (int k = 0; k < n_src; k++)
         if ((rc = pack_source(srcs + k, first_ray, n_rays_each, list[(size_t)k]))) return rc;

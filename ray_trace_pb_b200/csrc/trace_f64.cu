@@ -105,7 +105,7 @@ __device__ __forceinline__ void plain_surface_step(const TraceParams &P, const d
 // FROM_SOURCE rays are produced by the on-device source instead of being read from memory.
 // MODE        0: only the final slab is stored; 1: general (any slab selection, fused reductions); 2: general, as a
 //             sweep over P.n_src sources (FROM_SOURCE only): blockIdx.y picks the source, its output rows and its
-//             reduction bucket.
+//             reduction bucket; 3: general with RTB_FLAG_INTERSECT_ONLY (Surface.get_intersect: no front-side cull).
 // VARIANT     0: the plain hot loop (Optimistic); 1: the launch carries surface hints (rtb_surface.hints): the hot loop
 //             runs on OptimisticFlatZ; 2: every normal / axis of the system is exactly +-z: OptimisticAxial.
 template <bool USE_TABLE, bool FROM_SOURCE, int MODE, int VARIANT>
@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
     const DevReduce &red = sweep_reduce(P, s_sweep);
     const long long row0 = SWEEP ? (long long)blockIdx.y * P.n_rays : 0;
     const bool reducing = GENERAL && P.red.slab >= 0;
-    const bool intersect_only = GENERAL && (P.flags & RTB_FLAG_INTERSECT_ONLY) != 0;
+    // (a compile-time fact, not a flag test: the front-side cull it switches sits in the middle of every refracting
+    // step, and a warp-uniform branch there splits the step's basic block -- 1.4 % of the general kernel, 4 % of the OPM)
+    constexpr bool intersect_only = MODE == 3;
     Tally tally;
     if (GENERAL) tally_init(tally);
 
@@ -411,6 +413,7 @@ static cudaError_t launch_trace_f64_plain(const TraceParams &P, int sm_count, cu
     const bool table = P.n_wl > 0;
     const bool source = P.src.kind >= 0;
 #if RTB_TU_VARIANT != 2
+    if (sweep && (P.flags & RTB_FLAG_INTERSECT_ONLY)) return cudaErrorNotSupported;   // (refused by rtb_trace_sources)
     if (sweep)
         return table ? launch_one<true, true, 2>(P, (unsigned)blocks, stream)
                      : launch_one<false, true, 2>(P, (unsigned)blocks, stream);
@@ -422,6 +425,10 @@ static cudaError_t launch_trace_f64_plain(const TraceParams &P, int sm_count, cu
         return source ? launch_one<false, true, 0>(P, b, stream) : launch_one<false, false, 0>(P, b, stream);
     }
 #if RTB_TU_VARIANT != 2
+    if (P.flags & RTB_FLAG_INTERSECT_ONLY) {
+        if (table) return source ? launch_one<true, true, 3>(P, b, stream) : launch_one<true, false, 3>(P, b, stream);
+        return source ? launch_one<false, true, 3>(P, b, stream) : launch_one<false, false, 3>(P, b, stream);
+    }
     if (table) return source ? launch_one<true, true, 1>(P, b, stream) : launch_one<true, false, 1>(P, b, stream);
     return source ? launch_one<false, true, 1>(P, b, stream) : launch_one<false, false, 1>(P, b, stream);
 #else
