@@ -105,6 +105,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.t_mark = 0.0
 
     def start(self):
         try:
@@ -116,7 +117,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark(self):
+        """the timed region starts now: only samples that arrive from here on are reported"""
+        self.t_mark = time.monotonic()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -127,7 +132,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
-        for line in self.lines:
+        for t_line, line in self.lines:
+            if t_line < self.t_mark:
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -289,14 +296,25 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-
-    # ---- timed region -----------------------------------------------------------------------------------------
+    # nvidia-smi takes a few hundred ms to deliver its first sample: it is started before the warm-up so that samples
+    # are already flowing (every 20 ms) when the timed region begins; only those taken inside the region are reported
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if rank == 0:
+        deadline = time.monotonic() + 2.0
+        while not sampler.lines and sampler.proc is not None and time.monotonic() < deadline:
+            # (still warm-up, this rank only -- no collective) keep the GPU under load until the first sample is in
+            dev.trace_tensor(system.surfaces, materials, rays, keep="last", wavelengths=[WAVELENGTH], reducer=reducer,
+                             out=out)
+            torch.cuda.synchronize()
+
+    # ---- timed region -----------------------------------------------------------------------------------------
+    if rank == 0:
+        sampler.mark()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
