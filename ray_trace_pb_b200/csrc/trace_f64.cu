@@ -105,7 +105,9 @@ __device__ __forceinline__ void plain_surface_step(const TraceParams &P, const d
 // FROM_SOURCE rays are produced by the on-device source instead of being read from memory.
 // MODE        0: only the final slab is stored; 1: general (any slab selection, fused reductions); 2: general, as a
 //             sweep over P.n_src sources (FROM_SOURCE only): blockIdx.y picks the source, its output rows and its
-//             reduction bucket; 3: general with RTB_FLAG_INTERSECT_ONLY (Surface.get_intersect: no front-side cull).
+//             reduction bucket; 3: general with RTB_FLAG_INTERSECT_ONLY (Surface.get_intersect: no front-side cull);
+//             4: the final slab (or nothing) is stored and ONE after-surface slab is reduced -- the pupil-grid /
+//             spot-statistics workload -- on the final-slab kernel's loop, run in two legs around the sample.
 // VARIANT     0: the plain hot loop (Optimistic); 1: the launch carries surface hints (rtb_surface.hints): the hot loop
 //             runs on OptimisticFlatZ; 2: every normal / axis of the system is exactly +-z: OptimisticAxial.
 template <bool USE_TABLE, bool FROM_SOURCE, int MODE, int VARIANT>
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
 {
     using Optimistic = std::conditional_t<VARIANT == 1, OptimisticFlatZ,
                                           std::conditional_t<VARIANT == 2, OptimisticAxial, rtb::Optimistic>>;
-    constexpr bool GENERAL = MODE >= 1;
+    constexpr bool FINAL_RED = MODE == 4;
+    constexpr bool GENERAL = MODE >= 1 && MODE <= 3;
     constexpr bool SWEEP = MODE == 2;
     static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
     // the index tables are sized at launch ((n_wl + 1) * (n_surf + 1) doubles each, typically a few hundred bytes):
@@ -147,12 +150,12 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
     const DevSource &source = sweep_source(P, s_sweep);
     const DevReduce &red = sweep_reduce(P, s_sweep);
     const long long row0 = SWEEP ? (long long)blockIdx.y * P.n_rays : 0;
-    const bool reducing = GENERAL && P.red.slab >= 0;
+    const bool reducing = (GENERAL || FINAL_RED) && P.red.slab >= 0;
     // (a compile-time fact, not a flag test: the front-side cull it switches sits in the middle of every refracting
     // step, and a warp-uniform branch there splits the step's basic block -- 1.4 % of the general kernel, 4 % of the OPM)
     constexpr bool intersect_only = MODE == 3;
     Tally tally;
-    if (GENERAL) tally_init(tally);
+    if (GENERAL || FINAL_RED) tally_init(tally);
 
     const bool planes_in = (P.flags & RTB_FLAG_PLANES_IN) != 0, planes_out = (P.flags & RTB_FLAG_PLANES_OUT) != 0;
     const long long out_rows = P.out_stride / 8;
@@ -304,7 +307,26 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
             cur = after;
             n1 = n2;
         };
-        if (!GENERAL) {
+        if (FINAL_RED) {
+            RayLoop st;
+            st.cur = cur;
+            st.n1 = n1;
+            st.n2 = n2;
+            st.wl0 = wl0;
+            st.rcp_wl = rcp_wl;
+            st.row = row;
+            st.unlisted = unlisted;
+            st.dead = false;
+            st.force_careful = force_careful;
+            const int k_red = (P.red.slab - 2) >> 1;        // the sample is the slab after surface k_red
+#pragma unroll 1
+            for (; k <= k_red && !st.dead; k++) plain_surface_step<Optimistic, USE_TABLE>(P, s_ntab, s_ratio, s_c, k, st);
+            if (!st.dead) reduce_sample(red, st.cur, tally);
+#pragma unroll 1
+            for (; k < P.n_surf && !st.dead; k++) plain_surface_step<Optimistic, USE_TABLE>(P, s_ntab, s_ratio, s_c, k, st);
+            cur = st.cur;
+            dead = st.dead;
+        } else if (!GENERAL) {
             // two surfaces per trip: the ray's registers ping-pong between the two copies of the body instead of
             // being moved back at the end of every surface (+3 % here; the general mode's loop loses by it)
 #pragma unroll 1
@@ -352,12 +374,19 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
                 if (act & 2) store_ray(P.out + P.slab_pos[2 * k + 2] * P.out_stride, row0 + i, out_rows, planes_out, blank);
             }
         }
-        if (!GENERAL) {
+        if (!GENERAL && (!FINAL_RED || P.any_store)) {
             if (dead) set_nan(cur);
             store_ray(P.out, i, out_rows, planes_out, cur);
         }
     }
-    if (GENERAL && reducing) tally_flush(red, tally);
+    if ((GENERAL || FINAL_RED) && reducing) tally_flush(red, tally);
+}
+
+// MODE 4's shape: no sweep, no intersect-only, the final slab or nothing stored, one reduction at an after-surface slab
+bool final_slab_plus_one_reduction(const TraceParams &P)
+{
+    return P.n_src == 0 && (P.flags & RTB_FLAG_INTERSECT_ONLY) == 0 && P.red.slab >= 2 && (P.red.slab & 1) == 0 &&
+           (P.store_last_only || !P.any_store);
 }
 
 template <bool T, bool S, int M>
@@ -396,7 +425,7 @@ cudaError_t launch_trace_f64(const TraceParams &P, int sm_count, cudaStream_t st
     if (hinted) return launch_trace_f64_hinted(P, sm_count, stream);
     // (only the final-slab kernel gains from the axial form: +2.8 %; the general kernel loses 1.7 % and keeps the plain one)
     const bool final_slab_only = P.n_src == 0 && P.store_last_only && P.red.slab < 0 && (P.flags & RTB_FLAG_INTERSECT_ONLY) == 0;
-    if (axial && final_slab_only) return launch_trace_f64_axial(P, sm_count, stream);
+    if (axial && (final_slab_only || final_slab_plus_one_reduction(P))) return launch_trace_f64_axial(P, sm_count, stream);
     return launch_trace_f64_plain(P, sm_count, stream);
 }
 
@@ -420,6 +449,13 @@ static cudaError_t launch_trace_f64_plain(const TraceParams &P, int sm_count, cu
 #endif
     const bool fast = P.store_last_only && P.red.slab < 0 && (P.flags & RTB_FLAG_INTERSECT_ONLY) == 0;
     const unsigned b = (unsigned)blocks;
+#if RTB_TU_VARIANT == 2
+    // (measured: +6 % on axial systems; on tilted or hinted ones the general kernel is 5 % faster and keeps the job)
+    if (final_slab_plus_one_reduction(P)) {
+        if (table) return source ? launch_one<true, true, 4>(P, b, stream) : launch_one<true, false, 4>(P, b, stream);
+        return source ? launch_one<false, true, 4>(P, b, stream) : launch_one<false, false, 4>(P, b, stream);
+    }
+#endif
     if (fast) {
         if (table) return source ? launch_one<true, true, 0>(P, b, stream) : launch_one<true, false, 0>(P, b, stream);
         return source ? launch_one<false, true, 0>(P, b, stream) : launch_one<false, false, 0>(P, b, stream);
