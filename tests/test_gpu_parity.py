@@ -523,6 +523,47 @@ def test_final_slab_plus_reduction_mode(rt, rtm, oracle, dev, torch):
     np.testing.assert_allclose(fast.stats()["raw"], general.stats()["raw"], rtol=1e-12, atol=1e-9)
 
 
+def test_final_slab_plus_reduction_on_an_axial_system(rt, rtm, oracle, dev, torch):
+    """the same shape on a system whose every axis is +-z (the bench's relay): this is what the dedicated kernel
+    (MODE 4: the final-slab loop in two legs around the sample) runs; rays die before, at and after the sampled surface"""
+    system = systems.relay10_system(rt, rtm)
+    m_in = m_out = rtm.Vacuum()
+    mats = [m_in] + list(system.materials) + [m_out]
+    rays_np = systems.lattice_rays(220, 22.0, 0.0, 0.785, tilt=(0.03, 0.0))      # walks off: rays die at surfaces 0, 3, 4, 5
+    rays_np[::5, 7] = 0.6328                      # a second wavelength; every 11th ray arrives dead
+    rays_np[::11, 0] = np.nan
+    rays = torch.from_numpy(rays_np).cuda()
+    n_slabs = 2 * len(system.surfaces) + 1
+    want_hist = oracle.ray_trace(system, rays_np, m_in, m_out, n_threads=8)
+    dead = [int(np.isnan(want_hist[j, :, 0]).sum()) for j in (0, 2, 8, 10, 12)]
+    assert 0 < dead[0] < dead[1] < dead[2] < dead[3] < dead[4] < rays_np.shape[0], dead
+    for slab in (2, 10, n_slabs - 1):
+        for keep in ("last", "none"):
+            for wavelengths in ("auto", None):                               # host table / in-kernel Sellmeier
+                fast = dev.Reducer(slab, origin=(5.0, 0.0, 0.0), grid_n=64, half_width=30.0)
+                last = dev.trace_tensor(system.surfaces, mats, rays, keep=keep, reducer=fast, wavelengths=wavelengths)
+                if keep == "last":
+                    parity.assert_bit_identical(last.cpu().numpy()[0], want_hist[-1], f"final slab, reduction at {slab}")
+                else:
+                    assert last is None
+                want = oracle.reduce_stats(want_hist[slab], (5.0, 0.0, 0.0), (1, 0, 0), (0, 1, 0))
+                got = fast.stats_t.cpu().numpy()
+                assert got[0] == want[0] > 1000
+                np.testing.assert_allclose(got[1:8], want[1:8], rtol=1e-10, atol=1e-6)
+                np.testing.assert_allclose(got[8:], want[8:], rtol=1e-13)
+                assert np.array_equal(fast.grid.cpu().numpy()[2],
+                                      oracle.reduce_grid(want_hist[slab], (5.0, 0.0, 0.0), (1, 0, 0), (0, 1, 0), 64, 30.0)[2])
+    # generated rays
+    src = dev.RaySource.grid([5.0, 0, 0.0], 26.0, 301, 0.785)
+    s_hist = oracle.trace(system.surfaces, mats, src.generate().cpu().numpy(), keep_all=True, n_threads=8)
+    fast = dev.Reducer(10, origin=(5.0, 0.0, 0.0))
+    last = dev.trace_source(system.surfaces, mats, src, keep="last", reducer=fast)
+    parity.assert_bit_identical(last.cpu().numpy()[0], s_hist[-1], "source, final slab")
+    want = oracle.reduce_stats(s_hist[10], (5.0, 0.0, 0.0), (1, 0, 0), (0, 1, 0))
+    assert fast.stats_t.cpu().numpy()[0] == want[0]
+    np.testing.assert_allclose(fast.stats_t.cpu().numpy()[1:8], want[1:8], rtol=1e-10, atol=1e-6)
+
+
 def test_fused_reductions(rt, rtm, oracle, dev, torch):
     system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
     mats = [m_in] + system.materials + [m_out]
