@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 1
+#define RTB_ABI_VERSION 2 /* 2: rtb_surface.hints (was reserved), rtb_measure_dfma_chain_rate */
 /* per launch (the prescription travels in the kernel parameter block); the host layer chains longer systems */
 #define RTB_MAX_SURFACES 64
 #define RTB_MAX_WAVELENGTHS 8 /* rows of the host refractive-index table (one extra row answers NaN wavelengths) */

@@ -18,7 +18,7 @@ import os
 # RTB_LIBRARY_PATH selects another build of the same library (used to A/B kernel variants on the GPU box)
 LIB_PATH = Path(os.environ.get("RTB_LIBRARY_PATH") or (Path(__file__).resolve().parent / "_lib" / "librtb.so"))
 
-RTB_ABI_VERSION = 1
+RTB_ABI_VERSION = 2
 RTB_MAX_SURFACES = 64
 RTB_MAX_WAVELENGTHS = 8
 RTB_N_STATS = 12
