@@ -329,7 +329,6 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) trace_f64_kern
         } else if (!GENERAL) {
             // two surfaces per trip: the ray's registers ping-pong between the two copies of the body instead of
             // being moved back at the end of every surface (+3 % here; the general mode's loop loses by it)
-#pragma unroll 1
             RayLoop st;
             st.cur = cur;
             st.n1 = n1;
@@ -401,8 +400,8 @@ cudaError_t launch_one(const TraceParams &P, unsigned blocks, cudaStream_t strea
 } // namespace
 
 // launchers used by rtb_api.cu.  This file is compiled three times (Makefile): RTB_TU_VARIANT = 0 gives the plain kernels
-// (and launch_trace_f64, which picks), 1 those of launches that carry surface hints, 2 the final-slab kernels for
-// systems whose every normal and axis is exactly +-z -- three translation units that build in parallel.
+// (and launch_trace_f64, which picks), 1 those of launches that carry surface hints, 2 the final-slab kernels (MODE 0
+// and MODE 4) for systems whose every normal and axis is exactly +-z -- three translation units that build in parallel.
 #if RTB_TU_VARIANT == 1
 cudaError_t launch_trace_f64_hinted(const TraceParams &P, int sm_count, cudaStream_t stream)
 #elif RTB_TU_VARIANT == 2
