@@ -178,9 +178,27 @@ def cpu_baseline_run(n_threads: int, target_seconds: float = 12.0):
     return best, f"{side}x{side} = {side * side} rays x {N_SURFACES} surfaces, final slab only, best of 2"
 
 
+WORKLOAD = ("relay10 (BASELINE config 5 system): 10-surface achromat relay, 0.785 um, collimated Cartesian bundle, "
+            "final slab + fused pupil reduction")
+
+
+def numpy_leg(procs: int, reps: int, budget_s: float, rays: int = 1_000_000):
+    """The UNMODIFIED reference's NumPy path (baseline/_ref, installed by baseline/install_ref.sh) on the host cores:
+    SURVEY.md 8d "CPU baseline timing".  Runs in fresh interpreters (baseline/numpy_leg.py): nothing of this
+    framework is imported there."""
+    script = ROOT / "baseline" / "numpy_leg.py"
+    try:
+        r = subprocess.run([sys.executable, str(script), "--rays", str(rays), "--procs", str(procs), "--reps", str(reps),
+                            "--budget-s", str(budget_s)], capture_output=True, text=True, timeout=900)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as exc:                                    # reported, never fatal: it is a baseline
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores (oracle port; the reference is pure Python and
-    cannot travel to the GPU box)."""
+    """--impl reference: the reference's algorithm on all host cores.  `value` is the C restatement (oracle/rt_oracle.c,
+    OpenMP) -- some 40x faster per core than the reference's own NumPy code, i.e. the harder baseline; the unmodified
+    NumPy path on the same cores is reported next to it (cpu_baseline.numpy_allcores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -203,13 +221,15 @@ def run_reference(args):
         go()
     dt = time.perf_counter() - t0
     value = rays.shape[0] * N_SURFACES * args.steps / dt
-    sample = f"{side}x{side} = {rays.shape[0]} rays x {N_SURFACES} surfaces per step, final slab only"
+    sample = (f"a bounded sample of the same bundle per step: {side}x{side} = {rays.shape[0]} rays x {N_SURFACES} surfaces "
+              f"(same system, same wavelength, same 12 mm half-width; the final slab is produced, the pupil reduction -- "
+              f"3 atomics per ray on the GPU -- is not part of the CPU arm)")
     line = {"impl": "reference", "metric": "ray_surfaces_per_s_fp64", "value": value, "unit": "ray*surfaces/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "relay10 (BASELINE config 5 system): 10-surface achromat relay, 0.785 um, "
-                                   "collimated Cartesian bundle", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "ray*surfaces/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "ray*surfaces/s", "cores": cores, "kind": "port", "sample": sample,
+                             "numpy_allcores": numpy_leg(cores, 2, 15.0)},
             "e2e": {"value": value, "unit": "ray*surfaces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -424,8 +444,7 @@ def main():
             "metric": "ray_surfaces_per_s_fp64", "value": value, "unit": "ray*surfaces/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "relay10 (BASELINE config 5 system): 10-surface achromat relay, 0.785 um, "
-                                   "collimated Cartesian bundle, final slab + fused pupil reduction",
+            "config": {"workload": WORKLOAD,
                        "rays_total": source.n_rays, "rays_rank0": n_rays, "surfaces": N_SURFACES, "keep": "last", "reduce": args.reduce,
                        "grid": GRID_N if args.reduce == "grid" else 0,
                        "l2": "inputs (8 GB/GPU at the default size) are larger than L2; no flush needed",
@@ -468,7 +487,10 @@ def main():
             os.sched_setaffinity(0, all_cpus)               # the CPU baseline gets every core of the box again
             cores = len(all_cpus)
             v, sample = cpu_baseline_run(cores)
-            line["cpu_baseline"] = {"value": v, "unit": "ray*surfaces/s", "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": v, "unit": "ray*surfaces/s", "cores": cores, "kind": "port", "sample": sample,
+                                    # the reference's own NumPy code (unmodified, baseline/_ref), 1 core and all cores
+                                    "numpy_1core": numpy_leg(1, 2, 20.0),
+                                    "numpy_allcores": numpy_leg(cores, 3, 20.0)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

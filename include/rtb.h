@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 2 /* 2: rtb_surface.hints (was reserved), rtb_measure_dfma_chain_rate */
+#define RTB_ABI_VERSION 3 /* 2: rtb_surface.hints (was reserved), rtb_measure_dfma_chain_rate; 3: rtb_tune */
 /* per launch (the prescription travels in the kernel parameter block); the host layer chains longer systems */
 #define RTB_MAX_SURFACES 64
 #define RTB_MAX_WAVELENGTHS 8 /* rows of the host refractive-index table (one extra row answers NaN wavelengths) */
@@ -225,6 +225,16 @@ const char *rtb_last_error(void);
 int rtb_device_count(void);
 /* kernels launched by this library in this process so far (for bench.py's gpu_launches claim) */
 int64_t rtb_launch_count(void);
+
+/*
+ * Tuning knobs (never change a result, only which kernel gets there):
+ *   "lean_min_rays"  launches of at least this many rays that keep only the final slab and / or one after-surface
+ *                    reduction run the probe + lean kernel pair (csrc/trace_lean.cu); default 32768, negative = never.
+ *                    The environment variable RTB_LEAN_MIN_RAYS sets the initial value.
+ *   "host_fail_chunk" test hook: rtb_trace_host returns RTB_ERR_CUDA when it is about to launch chunk n (0-based) of a
+ *                    call (negative = off), after draining every copy already in flight.
+ */
+int rtb_tune(const char *key, int64_t value);
 
 /* ---- the hot path: replaces System.ray_trace, raytrace.py:641-661 --------------------------------------- */
 /*

@@ -18,7 +18,7 @@ import os
 # RTB_LIBRARY_PATH selects another build of the same library (used to A/B kernel variants on the GPU box)
 LIB_PATH = Path(os.environ.get("RTB_LIBRARY_PATH") or (Path(__file__).resolve().parent / "_lib" / "librtb.so"))
 
-RTB_ABI_VERSION = 2
+RTB_ABI_VERSION = 3
 RTB_MAX_SURFACES = 64
 RTB_MAX_WAVELENGTHS = 8
 RTB_N_STATS = 12
@@ -88,7 +88,7 @@ EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_
            "rtb_trace_host", "rtb_trace_source", "rtb_trace_sources", "rtb_generate_device", "rtb_reduce_init",
            "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_dfma_chain_rate",
            "rtb_measure_copy_bandwidth", "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
-           "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device"]
+           "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device", "rtb_tune"]
 
 
 def lib():
@@ -127,6 +127,8 @@ def lib():
     L.rtb_measure_dfma_rate.argtypes = [i32, dp, dp]
     L.rtb_measure_dfma_chain_rate.argtypes = [i32, i32, dp, dp]
     L.rtb_measure_copy_bandwidth.argtypes = [i32, i64, dp]
+    L.rtb_tune.argtypes = [C.c_char_p, i64]
+    L.rtb_tune.restype = i32
     L.rtb_host_alloc.argtypes = [C.c_size_t]
     L.rtb_host_alloc.restype = vp
     L.rtb_host_free.argtypes = [vp]

@@ -1,0 +1,172 @@
+// lean_steps.cuh -- the refracting steps of the "lean" trace kernel (trace_lean.cu): the same roundings as
+// surface_steps.cuh (reference raytrace.py:1160-1234, 1323-1347, 1467-1535, 241-306), arranged for the B200's
+// operand-read port.
+//
+// What binds the exact fp64 trace on this chip (tools/ubench/fp64_switch.cu, rf_bandwidth.cu):
+// a sub-partition reads ONE 64-bit register operand (an even/odd register pair) per cycle, for every pipe.  A DADD /
+// DMUL of two registers occupies the port for 2 cycles (= the FP64 pipe's own 2 cycles), a DFMA of three distinct
+// registers for 3, and every integer / select / move instruction in between for 1 or 2 more -- cycles per ray are the
+// SUM of those, not the maximum.  So these steps
+//   * read the prescription as warp-uniform operands (the surface loop's index is uniform, constants come from the
+//     constant bank / uniform registers and cost no port cycle),
+//   * update the ray in place (no second copy of the state, no register moves at the loop's back edge),
+//   * turn +-1 multiplications and np.sign selects into one integer operation on the sign bit,
+//   * pick the sphere's root before it is computed (one subtraction instead of two roots and two selects),
+//   * collect every domain test into one predicate with chained compares, and carry NO in-line handling of exact
+//     zeros: a ray whose flag comes back false is re-traced from its launch state by the careful per-surface
+//     machinery of surface_steps.cuh (trace_lean.cu: redo_ray), and surfaces where whole bundles produce zeros are
+//     found by a probe launch and run the zero-tolerant steps of surface_steps.cuh instead (policy mask).
+// A true flag means every intermediate was an ordinary normal number, so every rounding below is the one the
+// reference performs and the results are the same bits.  Steps exist for surfaces whose normal / input axis is
+// exactly (0, 0, +-1); any other surface runs the general steps of surface_steps.cuh.
+#pragma once
+
+#include "exact_math.cuh"
+#include "rtb_device.cuh"
+#include "surface_steps.cuh"
+
+namespace rtb {
+namespace lean {
+
+struct State {          // the loop-carried ray: wavelength and its reciprocal live outside
+    double ox, oy, oz;
+    double dx, dy, dz;
+    double ph;
+};
+
+// mag (>= +0, not NaN) with the sign bit of s XOR-ed in: mag * (+-1) and np.sign(s) * mag for s != 0
+__device__ __forceinline__ double with_sign_of(double mag, double s)
+{
+    return __hiloint2double(__double2hiint(mag) ^ (__double2hiint(s) & (int)0x80000000), __double2loint(mag));
+}
+
+__device__ __forceinline__ double sqrt_chk(bool &ok, double x)
+{
+    const int probe = __double2hiint(x) + (int)0xfcb00000;
+    ok &= (unsigned)probe < 0x7ca00000u;
+    return xm::sqrt_core(x, probe);
+}
+
+// |v|^2 -> |v| for a vector that is then divided by |v| (see Optimistic::sqrt_unit: requires 2^-969 <= |v|^2 < 2^104)
+__device__ __forceinline__ double sqrt_unit_chk(bool &ok, double x)
+{
+    const int probe = __double2hiint(x) + (int)0xfcb00000;
+    ok &= (unsigned)probe < 0x43200000u;
+    return xm::sqrt_core(x, probe);
+}
+
+// v / |v| with l = sqrt_unit_chk(|v|^2): quotients of numerators >= 2^-969 are normal (Optimistic::rcp_unit / divz_unit
+// without the zero forms: an exactly zero component fails the flag)
+__device__ __forceinline__ void unit3(bool &ok, double &x, double &y, double &z, double l)
+{
+    const double r = xm::refine_rcp(l);
+    ok &= xm::num_ok(x) & xm::num_ok(y) & xm::num_ok(z);
+    x = xm::div_core(x, l, r);
+    y = xm::div_core(y, l, r);
+    z = xm::div_core(z, l, r);
+}
+
+__device__ __forceinline__ void unit2(bool &ok, double &x, double &y, double l)
+{
+    const double r = xm::refine_rcp(l);
+    ok &= xm::num_ok(x) & xm::num_ok(y);
+    x = xm::div_core(x, l, r);
+    y = xm::div_core(y, l, r);
+}
+
+// SphericalSurface through RefractingSurface.propagate, input axis (0, 0, +-1).  `wl`, `wl_rcp`: the launch wavelength
+// (2^-100 <= |wl| <= 2^100, checked once per ray) and its refined reciprocal; `r_rcp`: refined 1/R, usable (checked per
+// block).  Returns "alive": on the sphere inside the aperture and not culled.  Updates the ray in place.
+__device__ __forceinline__ bool sphere_axial(bool &ok, const DevSurface &s, double r_rcp, State &r, double n1, double ratio,
+                                             double wl, double wl_rcp)
+{
+    // get_intersect (raytrace.py:1479-1516)
+    const double qx = r.ox - s.cx, qy = r.oy - s.cy, qz = r.oz - s.cz;
+    const double B = 2.0 * dot3(r.dx, r.dy, r.dz, qx, qy, qz);
+    const double C = sumsq3(qx, qy, qz) - s.radius_sq;
+    const double root = sqrt_chk(ok, B * B - 4.0 * C);
+    // The smaller root 0.5 * (-B - root) is negative exactly when root > -B (halving is exact, the difference of two
+    // doubles of this size cannot underflow): then the larger one is taken.  0.5 * ((+-root) - B) is the same addition
+    // the reference performs, so one of them is computed instead of two plus selects.  Both negative: no hit, flag.
+    const double sroot = __hiloint2double(__double2hiint(root) ^ ((root > -B) ? 0 : (int)0x80000000), __double2loint(root));
+    const double t = 0.5 * (sroot - B);
+    ok &= t >= 0.0;
+    const double px = r.ox + r.dx * t, py = r.oy + r.dy * t, pz = r.oz + r.dz * t;
+    const double len = sqrt_chk(ok, sumsq3(px - r.ox, py - r.oy, pz - r.oz));
+    // (len * 2 pi) / wl: numerator in [2^-482, 2^515], quotient normal for the wavelengths admitted -- no range tests
+    r.ph = r.ph + xm::div_core(len * kTwoPi, wl, wl_rcp) * n1;
+    // get_normal (raytrace.py:1476) and is_pt_on_surface (1518-1535)
+    const double rx = px - s.cx, ry = py - s.cy, rz = pz - s.cz;
+    ok &= xm::num_ok(rx) & xm::num_ok(ry) & xm::num_ok(rz);
+    const double nx = xm::div_core(rx, s.radius, r_rcp), ny = xm::div_core(ry, s.radius, r_rcp),
+                 nz = xm::div_core(rz, s.radius, r_rcp);
+    const double s_on = sumsq3(rx, ry, rz);
+    const double s_ap = px * px + py * py;
+    // (bitwise, not short-circuit: four chained compares instead of branches around them)
+    const bool on = (s_on >= s.on_sq_lo) & (s_on <= s.on_sq_hi) & (s_ap <= s.ap_sq_max) &
+                    !(r.dz * s.az < 0.0);                  // front-side cull, raytrace.py:1187-1192
+    // Snell (raytrace.py:1197-1216)
+    double bx = r.dy * nz - r.dz * ny;
+    double by = r.dz * nx - r.dx * nz;
+    double bz = r.dx * ny - r.dy * nx;
+    unit3(ok, bx, by, bz, sqrt_unit_chk(ok, sumsq3(bx, by, bz)));
+    double cx = ny * bz - nz * by;
+    double cy = nz * bx - nx * bz;
+    double cz = nx * by - ny * bx;
+    unit3(ok, cx, cy, cz, sqrt_unit_chk(ok, sumsq3(cx, cy, cz)));
+    const double mag_nc = ratio * dot3_np(cx, cy, cz, r.dx, r.dy, r.dz);
+    const double cosn = dot3(nx, ny, nz, r.dx, r.dy, r.dz);
+    ok &= (cosn != 0.0);                                   // np.sign(0) = 0: left to the careful path
+    const double w = with_sign_of(sqrt_chk(ok, 1.0 - mag_nc * mag_nc), cosn);
+    r.dx = mag_nc * cx + w * nx;
+    r.dy = mag_nc * cy + w * ny;
+    r.dz = mag_nc * cz + w * nz;
+    r.ox = px; r.oy = py; r.oz = pz;
+    return on;
+}
+
+// FlatSurface through RefractingSurface.propagate, normal (+-0, +-0, +-1) and input axis (0, 0, +-1).
+// With that normal the reference's arithmetic collapses exactly (x - (+-0) = x, (+-0) - x = -x, x + (+-0) = x for
+// x != 0; every such x is checked non-zero through the flag):
+//   t        = -((oz - cz) nz) / (dz nz)                                   (to_plane's axis shortcut)
+//   d x n    = (dy nz, -(dx nz), +-0)            n x nb = (-(nz nb_y), nz nb_x, +-0)
+//   nc . d   = nc_x dx + nc_y dy  (same sign, no cancellation)              n . d = nz dz
+//   d'       = (m nc_x, m nc_y, w nz)
+// The signs of the exact zeros never reach a result.  A ray along the normal (d x n = 0), one that starts on the plane
+// (t = +-0) or lies in the x = 0 / y = 0 plane fails the flag.
+__device__ __forceinline__ bool flat_axial(bool &ok, const DevSurface &s, State &r, double n1, double ratio, double wl,
+                                           double wl_rcp)
+{
+    // propagate_ray2plane (raytrace.py:241-306) with exclude_backward_propagation (303-304)
+    const double num = (r.oz - s.cz) * s.nz;
+    const double den = r.dz * s.nz;
+    const double den_rcp = xm::refine_rcp(den);
+    const double t = xm::div_core(-num, den, den_rcp);
+    ok &= xm::den_ok(den) & xm::quo_ok(den_rcp) & xm::num_ok(num) & xm::quo_ok(t);
+    const double vx = r.dx * t, vy = r.dy * t, vz = r.dz * t;
+    const double px = r.ox + vx, py = r.oy + vy, pz = r.oz + vz;
+    const double len = with_sign_of(sqrt_chk(ok, sumsq3(vx, vy, vz)), t);      // * prop_direction; t != 0 here
+    r.ph = r.ph + xm::div_core(len * kTwoPi, wl, wl_rcp) * n1;
+    // is_pt_on_surface (raytrace.py:1339-1347), front-side cull (1187-1192)
+    const double rx = px - s.cx, ry = py - s.cy, rz = pz - s.cz;
+    const bool on = !(t < 0.0) & (fabs(rz * s.nz) < kOnSurfaceTol) & (sumsq3(rx, ry, rz) <= s.ap_sq_max) &
+                    !(r.dz * s.az < 0.0);
+    // Snell in the plane
+    double bx = r.dy * s.nz, by = -(r.dx * s.nz);
+    unit2(ok, bx, by, sqrt_unit_chk(ok, bx * bx + by * by));
+    double cx = -(s.nz * by), cy = s.nz * bx;
+    unit2(ok, cx, cy, sqrt_unit_chk(ok, cx * cx + cy * cy));
+    const double mag_nc = ratio * (cx * r.dx + cy * r.dy);
+    const double w = with_sign_of(sqrt_chk(ok, 1.0 - mag_nc * mag_nc), den);   // sign(n . d) = sign(nz dz), non-zero
+    const double ex = mag_nc * cx, ey = mag_nc * cy;
+    // m nc_x + w (+-0) keeps m nc_x only if it is not itself a zero: products this small leave the lean path
+    ok &= xm::num_ok(ex) & xm::num_ok(ey);
+    r.dx = ex;
+    r.dy = ey;
+    r.dz = w * s.nz;
+    r.ox = px; r.oy = py; r.oz = pz;
+    return on;
+}
+
+} // namespace lean
+} // namespace rtb

@@ -16,6 +16,8 @@
 namespace rtb {
 cudaError_t launch_trace_f64(const TraceParams &P, int sm_count, cudaStream_t stream);
 cudaError_t launch_trace_fast(const TraceParams &P, int precision, int sm_count, cudaStream_t stream);
+bool lean_eligible(const TraceParams &P);
+cudaError_t launch_trace_lean(const TraceParams &P, unsigned *counts, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t launch_generate(const DevSource &src, long long n_rays, double *out, int sm_count, cudaStream_t stream);
 cudaError_t launch_reduce_init(const DevReduce &red, int sm_count, cudaStream_t stream);
 cudaError_t launch_intersect(const double *r1, long long n1, const double *r2, long long n2, double *out,
@@ -38,6 +40,12 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+// launches of at least this many rays that keep only the final slab / one reduction go to the lean kernel (probe launch
+// + trace launch, trace_lean.cu); smaller ones are not worth a probe.  rtb_tune("lean_min_rays", n); negative = never.
+std::atomic<long long> g_lean_min_rays{32768};
+// test hook: rtb_trace_host fails (RTB_ERR_CUDA, "injected") when it is about to launch chunk number n (0-based) of a
+// call; negative = off.  rtb_tune("host_fail_chunk", n).  Lets the tests check that an error return leaves no copy in flight.
+std::atomic<long long> g_host_fail_chunk{-1};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -61,6 +69,7 @@ constexpr int kSlots = 3;
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    unsigned *lean_counts = nullptr;   // probe scratch of the lean kernel for this slot's chunks
     double *dev_in = nullptr;
     double *dev_out = nullptr;
     double *pin_in = nullptr;
@@ -349,10 +358,55 @@ int pack_source(const rtb_source *src, long long first, long long count, rtb::De
     return RTB_OK;
 }
 
-int launch(const rtb::TraceParams &P, int precision, int sm_count, cudaStream_t stream)
+int ensure_pool(DeviceCtx *ctx, int device)
 {
-    cudaError_t e = (precision == RTB_F64_EXACT) ? rtb::launch_trace_f64(P, sm_count, stream)
-                                                 : rtb::launch_trace_fast(P, precision, sm_count, stream);
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    if (!ctx->pool) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        RTB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+        unsigned long long keep = ~0ull;    // never hand the (few KB of) memory back between calls
+        RTB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    return RTB_OK;
+}
+
+bool wants_lean(const rtb::TraceParams &P, int precision)
+{
+    static const bool env_read = [] {
+        if (const char *env = getenv("RTB_LEAN_MIN_RAYS")) g_lean_min_rays.store(atoll(env), std::memory_order_relaxed);
+        return true;
+    }();
+    (void)env_read;
+    const long long min_rays = g_lean_min_rays.load(std::memory_order_relaxed);
+    return precision == RTB_F64_EXACT && min_rays >= 0 && P.n_rays >= min_rays && rtb::lean_eligible(P);
+}
+
+// `lean_counts`: probe scratch owned by the caller (the host pipeline's slots), or NULL to take it from the device's
+// stream-ordered pool for the duration of this launch.
+int launch(const rtb::TraceParams &P, int precision, DeviceCtx *ctx, int device, cudaStream_t stream,
+           unsigned *lean_counts = nullptr)
+{
+    if (P.n_rays > 0 && wants_lean(P, precision)) {
+        const size_t bytes = sizeof(unsigned) * 2 * rtb::kMaxSurfaces * (size_t)std::max(P.n_src, 1);
+        unsigned *counts = lean_counts;
+        if (!counts) {
+            int rc = ensure_pool(ctx, device);
+            if (rc) return rc;
+            if (cudaMallocFromPoolAsync((void **)&counts, bytes, ctx->pool, stream) != cudaSuccess)
+                return fail(RTB_ERR_NOMEM, "stream-ordered allocation of %zu bytes of probe scratch failed", bytes);
+        }
+        int launches = 0;
+        cudaError_t e = rtb::launch_trace_lean(P, counts, ctx->sm_count, stream, &launches);
+        if (!lean_counts) cudaFreeAsync(counts, stream);
+        if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString(e));
+        g_launches.fetch_add(launches, std::memory_order_relaxed);
+        return RTB_OK;
+    }
+    cudaError_t e = (precision == RTB_F64_EXACT) ? rtb::launch_trace_f64(P, ctx->sm_count, stream)
+                                                 : rtb::launch_trace_fast(P, precision, ctx->sm_count, stream);
     if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString(e));
     if (P.n_rays > 0) g_launches.fetch_add(1, std::memory_order_relaxed);
     return RTB_OK;
@@ -412,6 +466,20 @@ int rtb_device_count(void)
 
 int64_t rtb_launch_count(void) { return g_launches.load(); }
 
+int rtb_tune(const char *key, int64_t value)
+{
+    if (!key) return fail(RTB_ERR_INVALID, "key is NULL");
+    if (strcmp(key, "lean_min_rays") == 0) {
+        g_lean_min_rays.store(value, std::memory_order_relaxed);
+        return RTB_OK;
+    }
+    if (strcmp(key, "host_fail_chunk") == 0) {
+        g_host_fail_chunk.store(value, std::memory_order_relaxed);
+        return RTB_OK;
+    }
+    return fail(RTB_ERR_INVALID, "unknown tuning key '%s'", key);
+}
+
 int rtb_trace_device(const rtb_system *sys, const double *rays_in_dev, int64_t n_rays, double *out_dev,
                      const rtb_trace_opts *opts, int device, void *stream)
 {
@@ -429,7 +497,7 @@ int rtb_trace_device(const rtb_system *sys, const double *rays_in_dev, int64_t n
     P.out = out_dev;
     P.n_rays = n_rays;
     P.out_stride = 8 * (long long)n_rays;
-    return launch(P, opts->precision, ctx->sm_count, (cudaStream_t)stream);
+    return launch(P, opts->precision, ctx, device, (cudaStream_t)stream);
 }
 
 int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first_ray, int64_t n_rays,
@@ -448,7 +516,7 @@ int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first
     P.out = out_dev;
     P.n_rays = n_rays;
     P.out_stride = 8 * (long long)n_rays;
-    return launch(P, opts->precision, ctx->sm_count, (cudaStream_t)stream);
+    return launch(P, opts->precision, ctx, device, (cudaStream_t)stream);
 }
 
 int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_src, int64_t first_ray,
@@ -476,18 +544,7 @@ int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_s
     // it by the time the call returns, so the vector may go out of scope)
     rtb::DevSource *list_dev = nullptr;
     const size_t bytes = sizeof(rtb::DevSource) * (size_t)n_src;
-    {
-        std::lock_guard<std::mutex> lock(g_ctx_mutex);
-        if (!ctx->pool) {
-            cudaMemPoolProps props = {};
-            props.allocType = cudaMemAllocationTypePinned;
-            props.location.type = cudaMemLocationTypeDevice;
-            props.location.id = device;
-            RTB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
-            unsigned long long keep = ~0ull;    // never hand the (few KB of) memory back between calls
-            RTB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        }
-    }
+    if ((rc = ensure_pool(ctx, device))) return rc;
     if (cudaMallocFromPoolAsync((void **)&list_dev, bytes, ctx->pool, st) != cudaSuccess)
         return fail(RTB_ERR_NOMEM, "stream-ordered allocation of %zu bytes for the source list failed", bytes);
     cudaError_t e = cudaMemcpyAsync(list_dev, list.data(), bytes, cudaMemcpyHostToDevice, st);
@@ -502,7 +559,7 @@ int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_s
     P.out = out_dev;
     P.n_rays = n_rays_each;
     P.out_stride = 8 * (long long)n_rays_each * n_src;
-    rc = launch(P, opts->precision, ctx->sm_count, st);
+    rc = launch(P, opts->precision, ctx, device, st);
     cudaFreeAsync(list_dev, st);
     return rc;
 }
@@ -547,6 +604,7 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
         Slot &sl = ctx->slot[s];
         if (!sl.stream) RTB_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         if (!sl.done) RTB_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        if (!sl.lean_counts) RTB_CUDA(cudaMalloc((void **)&sl.lean_counts, sizeof(unsigned) * 2 * rtb::kMaxSurfaces));
         if ((rc = grow_dev(&sl.dev_in, &sl.dev_in_bytes, (size_t)chunk * row))) return rc;
         if (slabs > 0 && (rc = grow_dev(&sl.dev_out, &sl.dev_out_bytes, (size_t)chunk * row * slabs))) return rc;
         if (!in_pinned && (rc = grow_pin(&sl.pin_in, &sl.pin_in_bytes, (size_t)chunk * row))) return rc;
@@ -573,44 +631,74 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
         return RTB_OK;
     };
 
-    long long n_chunks = (n_rays + chunk - 1) / chunk;
-    for (long long c = 0; c < n_chunks; c++) {
-        const int s = (int)(c % kSlots);
-        if ((rc = retire(s))) return rc;
-        Slot &sl = ctx->slot[s];
-        const long long r0 = c * chunk;
-        const long long cnt = std::min<long long>(chunk, n_rays - r0);
-        const double *src = rays_in_host + (size_t)r0 * 8;
-        if (!in_pinned) {
-            memcpy(sl.pin_in, src, (size_t)cnt * row);
-            src = sl.pin_in;
-        }
-        RTB_CUDA(cudaMemcpyAsync(sl.dev_in, src, (size_t)cnt * row, cudaMemcpyHostToDevice, sl.stream));
-        P.rays_in = sl.dev_in;
-        P.out = sl.dev_out;
-        P.n_rays = cnt;
-        P.out_stride = 8 * cnt;
-        if ((rc = launch(P, opts->precision, ctx->sm_count, sl.stream))) return rc;
-        if (slabs > 0) {
-            if (out_pinned) {
-                // (slabs, cnt, 8) device -> rows [r0, r0+cnt) of every slab of the (slabs, N, 8) host array
-                RTB_CUDA(cudaMemcpy2DAsync(out_host + (size_t)r0 * 8, (size_t)n_rays * row, sl.dev_out,
-                                           (size_t)cnt * row, (size_t)cnt * row, (size_t)slabs,
-                                           cudaMemcpyDeviceToHost, sl.stream));
-            } else {
-                RTB_CUDA(cudaMemcpyAsync(sl.pin_out, sl.dev_out, (size_t)cnt * row * slabs, cudaMemcpyDeviceToHost,
-                                         sl.stream));
+    // cudaMemcpy2DAsync refuses pitches above cudaDevAttrMaxPitch (2^31 - 1 bytes: N >= 2^25 rays); then, and for a
+    // single slab, each slab's rows go out as one contiguous copy
+    int max_pitch = 0;
+    if (cudaDeviceGetAttribute(&max_pitch, cudaDevAttrMaxPitch, device) != cudaSuccess) max_pitch = 0;
+    const bool strided_copy_ok = slabs > 1 && (size_t)n_rays * row <= (size_t)max_pitch;
+
+    // Every error return below goes through drain(): copies into the caller's buffers that are still in flight must
+    // have landed (or failed) before the call returns, whatever it returns.
+    auto drain = [&]() {
+        for (int s = 0; s < kSlots; s++)
+            if (ctx->slot[s].stream) cudaStreamSynchronize(ctx->slot[s].stream);
+    };
+    auto cuda_failed = [&](cudaError_t e, const char *what) -> int {
+        if (e == cudaSuccess) return RTB_OK;
+        drain();
+        return fail(RTB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    auto run_pipeline = [&]() -> int {
+        const long long n_chunks = (n_rays + chunk - 1) / chunk;
+        for (long long c = 0; c < n_chunks; c++) {
+            const int s = (int)(c % kSlots);
+            if ((rc = retire(s))) return rc;
+            Slot &sl = ctx->slot[s];
+            const long long r0 = c * chunk;
+            const long long cnt = std::min<long long>(chunk, n_rays - r0);
+            const double *src = rays_in_host + (size_t)r0 * 8;
+            if (!in_pinned) {
+                memcpy(sl.pin_in, src, (size_t)cnt * row);
+                src = sl.pin_in;
             }
+            if ((rc = cuda_failed(cudaMemcpyAsync(sl.dev_in, src, (size_t)cnt * row, cudaMemcpyHostToDevice, sl.stream),
+                                  "copy-in")))
+                return rc;
+            P.rays_in = sl.dev_in;
+            P.out = sl.dev_out;
+            P.n_rays = cnt;
+            P.out_stride = 8 * cnt;
+            if (c == g_host_fail_chunk.load(std::memory_order_relaxed))
+                return fail(RTB_ERR_CUDA, "injected failure before the launch of chunk %lld (rtb_tune host_fail_chunk)", c);
+            if ((rc = launch(P, opts->precision, ctx, device, sl.stream, sl.lean_counts))) return rc;
+            if (slabs > 0) {
+                cudaError_t e = cudaSuccess;
+                if (!out_pinned) {
+                    e = cudaMemcpyAsync(sl.pin_out, sl.dev_out, (size_t)cnt * row * slabs, cudaMemcpyDeviceToHost, sl.stream);
+                } else if (strided_copy_ok) {
+                    // (slabs, cnt, 8) device -> rows [r0, r0+cnt) of every slab of the (slabs, N, 8) host array
+                    e = cudaMemcpy2DAsync(out_host + (size_t)r0 * 8, (size_t)n_rays * row, sl.dev_out, (size_t)cnt * row,
+                                          (size_t)cnt * row, (size_t)slabs, cudaMemcpyDeviceToHost, sl.stream);
+                } else {
+                    for (int j = 0; j < slabs && e == cudaSuccess; j++)
+                        e = cudaMemcpyAsync(out_host + ((size_t)j * n_rays + r0) * 8, sl.dev_out + (size_t)j * cnt * 8,
+                                            (size_t)cnt * row, cudaMemcpyDeviceToHost, sl.stream);
+                }
+                if ((rc = cuda_failed(e, "copy-out"))) return rc;
+            }
+            if ((rc = cuda_failed(cudaEventRecord(sl.done, sl.stream), "cudaEventRecord"))) return rc;
+            pending[s].active = true;
+            pending[s].r0 = r0;
+            pending[s].cnt = cnt;
         }
-        RTB_CUDA(cudaEventRecord(sl.done, sl.stream));
-        pending[s].active = true;
-        pending[s].r0 = r0;
-        pending[s].cnt = cnt;
-    }
-    // drain in issue order
-    for (long long c = n_chunks; c < n_chunks + kSlots; c++)
-        if ((rc = retire((int)(c % kSlots)))) return rc;
-    return RTB_OK;
+        // drain in issue order
+        for (long long c = n_chunks; c < n_chunks + kSlots; c++)
+            if ((rc = retire((int)(c % kSlots)))) return rc;
+        return RTB_OK;
+    };
+    rc = run_pipeline();
+    if (rc) drain();
+    return rc;
 }
 
 int rtb_generate_device(const rtb_source *src, int64_t first_ray, int64_t n_rays, double *rays_out_dev, int device,

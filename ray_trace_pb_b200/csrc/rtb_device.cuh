@@ -110,6 +110,13 @@ struct TraceParams {
     const DevSource *src_list;
     int32_t n_src;
     int32_t pad1;
+    // the lean kernel (trace_lean.cu): results of its probe launch, [source][surface][2] = {rays that reached the
+    // surface, rays whose lean step failed there}; surfaces that run the general steps whatever the probe says; and,
+    // for the probe launch itself, the sampling stride through the n_rays_total rays of the real launch
+    const unsigned *lean_counts;
+    unsigned long long lean_general;
+    long long lean_probe_stride;
+    long long lean_probe_total;
     DevSurface surf[kMaxSurfaces];
     DevMaterial mat[kMaxMedia];
     double wl[kMaxWavelengths];

@@ -1,0 +1,490 @@
+// trace_lean.cu -- the fused fp64 trace for the workloads that keep nothing but the final slab and / or ONE fused
+// reduction (spot statistics, pupil grid) after a surface: BASELINE configs 2-5, the bench step, every sweep.
+// Same results, bit for bit, as trace_f64.cu (tests/test_gpu_parity.py runs both); what differs is how the work is laid
+// out for the B200's operand-read port (lean_steps.cuh):
+//
+//   * The surface loop's trip count and index are warp-uniform -- a dead ray idles through the remaining surfaces instead
+//     of leaving the loop -- so the prescription is read through uniform registers / constant-bank operands.
+//   * The ray is updated in place by steps that carry no exact-zero handling and no second copy of the state.  A ray
+//     whose domain flag fails anywhere is re-traced from its launch state, once, after the loop, by the careful
+//     per-surface machinery of surface_steps.cuh (redo_ray, out of line).
+//   * Surfaces at which WHOLE BUNDLES fail the lean step (a collimated beam at its first lens: d x n has an exact zero
+//     component ray after ray; a source on the first flat; a beam along a flat's normal) are found by a probe launch of
+//     this same kernel over a sample of <= 2048 rays per source, which counts per surface the rays that reached it and the
+//     rays whose lean step failed; the main launch reads the counts and runs the zero-tolerant general steps
+//     (surface_steps.cuh, OptimisticZ) at those surfaces.  No host round trip: probe and trace are two launches on the
+//     caller's stream.  Hints (rtb_surface.hints) are therefore not needed by this kernel.
+//   * Spot statistics are tallied per thread in shared memory (touched once per ray) instead of in 24 registers.
+//
+// THIS TRANSLATION UNIT MUST BE COMPILED WITH -fmad=false (see trace_f64.cu).
+#include <cmath>
+#include <math_constants.h>
+
+#include "exact_math.cuh"
+#include "lean_steps.cuh"
+#include "rtb_device.cuh"
+#include "surface_steps.cuh"
+#include "trace_common.cuh"
+
+namespace rtb {
+
+namespace {
+
+#ifndef RTB_LEAN_THREADS
+#define RTB_LEAN_THREADS 128
+#endif
+#ifndef RTB_LEAN_MIN_BLOCKS
+#define RTB_LEAN_MIN_BLOCKS 7
+#endif
+constexpr int kLeanThreads = RTB_LEAN_THREADS;
+constexpr int kLeanMinBlocks = RTB_LEAN_MIN_BLOCKS;
+constexpr int kProbeRays = 2048;          // sample size of the probe launch, per source
+constexpr unsigned kProbeOneIn = 200;     // a surface runs the general steps when more than 1 in 200 probe rays failed
+
+// which step a surface runs (decided once per block: kind, axes, the reciprocal radius, the probe's counts)
+enum StepCode : int { kLeanSphere = 0, kLeanFlat = 1, kGeneralRefracting = 2, kGeneralMirror = 3, kGeneralLens = 4 };
+
+// per-surface facts every ray needs, decided once per block: one 16-byte shared-memory read per surface
+struct __align__(16) SurfaceShared {
+    double rcp;                           // refined 1/R (1/f for perfect lenses)
+    int code;                             // StepCode
+    int rcp_ok;                           // that reciprocal is usable by the optimistic steps
+};
+
+struct LeanShared {
+    SurfaceShared surf[kMaxSurfaces];
+};
+
+// ---- the careful whole-ray trace: a ray whose lean flag failed starts over here --------------------------------------
+// Returns the final slab's row (blanked when the ray is dead) and the row of slab 2 * k_sample + 2.
+template <bool USE_TABLE>
+static __device__ __noinline__ void redo_ray(const TraceParams *P, Ray cur, int k_sample, Ray *final_row, Ray *sample_row)
+{
+    const int n_med = P->n_surf + 1;
+    const double wl0 = cur.wl;
+    int row = 0;
+    bool unlisted = false;
+    if (USE_TABLE) {
+        row = P->n_wl;
+        const long long bits = __double_as_longlong(wl0);
+        for (int k = 0; k < P->n_wl; k++)
+            if (__double_as_longlong(P->wl[k]) == bits) row = k;
+        unlisted = (row == P->n_wl) && (wl0 == wl0);
+        row *= n_med;
+    }
+    auto index_of = [&](int medium) {
+        return !USE_TABLE ? eval_index(P->mat[medium], wl0)
+                          : (unlisted ? index_for_unlisted(&P->mat[medium], wl0) : P->n_tab[row + medium]);
+    };
+    double n1 = index_of(0);
+    bool dead = false;
+    Ray blank;
+    set_nan(blank);
+    *sample_row = blank;
+    for (int k = 0; k < P->n_surf; k++) {
+        if (!dead) {
+            const DevSurface *s = &P->surf[k];
+            const double n2 = index_of(k + 1);
+            StepResult res;
+            if (s->kind == RTB_SURF_FLAT || s->kind == RTB_SURF_SPHERE) {
+                const double ratio = (USE_TABLE && !unlisted) ? P->ratio_tab[row + k] : xm::div(n1, n2);
+                res = careful_refracting(s, cur, n1, ratio, true);
+            } else if (s->kind == RTB_SURF_MIRROR) {
+                res = careful_mirror(s, cur, n1);
+            } else {
+                res = careful_lens(s, cur, n1, n2, false);
+            }
+            cur = res.after;
+            dead = res.dead;
+            n1 = n2;
+        }
+        if (k == k_sample) *sample_row = dead ? blank : cur;
+    }
+    *final_row = dead ? blank : cur;
+}
+
+// ---- fused reductions: rtb_reduce in rtb.h (same arithmetic as reduce_sample in trace_common.cuh) --------------------
+// the per-thread tally lives in shared memory, [statistic][thread]
+__device__ __forceinline__ void accumulate(const DevReduce &R, double ox, double oy, double oz, double phase, double *tally)
+{
+    const double px = ox - R.ox, py = oy - R.oy, pz = oz - R.oz;
+    const double u = dot3(px, py, pz, R.e1x, R.e1y, R.e1z);
+    const double v = dot3(px, py, pz, R.e2x, R.e2y, R.e2z);
+    const double ph = phase - R.phase_ref;
+    if (!(isfinite(u) && isfinite(v) && isfinite(ph))) return;
+    if (R.stats) {
+        double *t = tally + threadIdx.x;
+        constexpr int W = kLeanThreads;
+        t[0 * W] += 1.0;
+        t[1 * W] += u;
+        t[2 * W] += v;
+        t[3 * W] += u * u;
+        t[4 * W] += v * v;
+        t[5 * W] += u * v;
+        t[6 * W] += ph;
+        t[7 * W] += ph * ph;
+        t[8 * W] = fmin(t[8 * W], u);
+        t[9 * W] = fmax(t[9 * W], u);
+        t[10 * W] = fmin(t[10 * W], v);
+        t[11 * W] = fmax(t[11 * W], v);
+    }
+    if (R.grid) {
+        const double fu = floor((u + R.half_width) * R.inv_cell);
+        const double fv = floor((v + R.half_width) * R.inv_cell);
+        const double g = (double)R.grid_n;
+        if (fu >= 0.0 && fu < g && fv >= 0.0 && fv < g) {
+            const long long cell = (long long)fv * R.grid_n + (long long)fu;
+            const long long plane = (long long)R.grid_n * R.grid_n;
+            double s, c;
+            sincos(ph, &s, &c);
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + cell), "d"(c) : "memory");
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + plane + cell), "d"(s) : "memory");
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + 2 * plane + cell), "d"(1.0) : "memory");
+        }
+    }
+}
+
+__device__ __noinline__ void flush_tally(const DevReduce &R, const double *tally)
+{
+    if (!R.stats) return;
+    __shared__ double part[12][kLeanThreads / 32];
+    constexpr int W = kLeanThreads;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < 12; k++) {
+        double x = tally[k * W + threadIdx.x];
+        x = (k < 8) ? warp_sum(x) : ((k == 8 || k == 10) ? warp_min(x) : warp_max(x));
+        if (lane == 0) part[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x;
+        double x = part[k][0];
+        for (int w = 1; w < kLeanThreads / 32; w++)
+            x = (k < 8) ? x + part[k][w] : ((k == 8 || k == 10) ? fmin(x, part[k][w]) : fmax(x, part[k][w]));
+        if (k < 8) {
+            if (x != 0.0) atomicAdd(R.stats + k, x);
+        } else if (k == 8 || k == 10) {
+            if (x < CUDART_INF) atomic_min_f64(R.stats + k, x);
+        } else {
+            if (x > -CUDART_INF) atomic_max_f64(R.stats + k, x);
+        }
+    }
+}
+
+// the general steps of surface_steps.cuh with their zero forms in line, on the lean kernel's in-place state
+__device__ __forceinline__ bool general_step(const DevSurface &s, int code, double rcp_y, bool rcp_ok, lean::State &r, double n1,
+                                             double n2, double ratio, double wl0, double wl_rcp, bool &ok)
+{
+    OptimisticZ m;
+    xm::Rcp rcp_wl, rcp_k;
+    rcp_wl.b = wl0; rcp_wl.y = wl_rcp; rcp_wl.ok = true;
+    rcp_k.b = (code == kGeneralLens) ? s.focal_len : s.radius;
+    rcp_k.y = rcp_y;
+    rcp_k.ok = rcp_ok;
+    Ray in, after;
+    in.ox = r.ox; in.oy = r.oy; in.oz = r.oz; in.dx = r.dx; in.dy = r.dy; in.dz = r.dz; in.ph = r.ph;
+    in.wl = wl0;
+    AtRaw raw;
+    bool dead;
+    if (code == kGeneralRefracting)
+        dead = refracting_step<OptimisticZ, false>(m, s, in, n1, ratio, rcp_wl, rcp_k, true, raw, after);
+    else if (code == kGeneralMirror)
+        dead = mirror_step<OptimisticZ, false>(m, s, in, n1, rcp_wl, raw, after);
+    else
+        dead = perfect_lens_step<OptimisticZ>(m, s, in, n1, n2, rcp_wl, rcp_k, false, false, raw, after);
+    ok = m.ok;
+    r.ox = after.ox; r.oy = after.oy; r.oz = after.oz;
+    r.dx = after.dx; r.dy = after.dy; r.dz = after.dz;
+    r.ph = after.ph;
+    return !dead;
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------------------
+// USE_TABLE / FROM_SOURCE as in trace_f64.cu.  SWEEP: blockIdx.y picks the source, its output rows and its reduction
+// bucket (rtb_trace_sources).  PROBE: the probe launch -- a strided sample of the rays, per-surface recovery, counts only.
+template <bool USE_TABLE, bool FROM_SOURCE, bool SWEEP, bool PROBE>
+__global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kernel(const __grid_constant__ TraceParams P,
+                                                                                  unsigned *probe_counts)
+{
+    static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
+    // dynamic shared memory: {n, n1/n2} pairs per (wavelength row, surface), then the per-thread tallies
+    extern __shared__ double s_dyn[];
+    const int n_med = P.n_surf + 1;
+    double *const s_pair = s_dyn;
+    double *const s_tally = s_dyn + (USE_TABLE ? 2 * (P.n_wl + 1) * n_med : 0);
+    __shared__ LeanShared s_c;
+    __shared__ SweepShared<SWEEP> s_sweep;
+    if (SWEEP) sweep_setup(P, s_sweep);
+    if (USE_TABLE) {
+        const int count = (P.n_wl + 1) * n_med;
+        for (int k = threadIdx.x; k < count; k += blockDim.x) {
+            s_pair[2 * k] = P.n_tab[k];
+            s_pair[2 * k + 1] = P.ratio_tab[k];
+        }
+    }
+    const bool reducing = !PROBE && P.red.slab >= 0;
+    if (reducing && P.red.stats) {
+        for (int k = 0; k < 12; k++)
+            s_tally[k * kLeanThreads + threadIdx.x] = (k < 8) ? 0.0 : ((k == 8 || k == 10) ? CUDART_INF : -CUDART_INF);
+    }
+    for (int k = threadIdx.x; k < P.n_surf; k += blockDim.x) {
+        const DevSurface &s = P.surf[k];
+        const double den = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
+        const double rcp = xm::refine_rcp(den);
+        const bool sane = xm::den_ok(den) && fabs(den) < 4503599627370496.0 && xm::quo_ok(rcp);
+        s_c.surf[k].rcp = rcp;
+        s_c.surf[k].rcp_ok = sane;
+        // a sphere whose reciprocal radius is unusable goes through the general step (which flags it for the careful path)
+        bool general = ((P.lean_general >> k) & 1ull) != 0 || (!sane && s.kind == RTB_SURF_SPHERE);
+        if (!PROBE && P.lean_counts) {
+            const unsigned *cnt = P.lean_counts + ((size_t)(SWEEP ? blockIdx.y : 0) * kMaxSurfaces + k) * 2;
+            general |= (unsigned long long)cnt[1] * kProbeOneIn > (unsigned long long)cnt[0];
+        }
+        int code = (s.kind == RTB_SURF_MIRROR) ? kGeneralMirror : (s.kind == RTB_SURF_PERFECT_LENS) ? kGeneralLens
+                                                                                                     : kGeneralRefracting;
+        if (!general) code = (s.kind == RTB_SURF_SPHERE) ? kLeanSphere : kLeanFlat;
+        s_c.surf[k].code = code;
+    }
+    __syncthreads();
+
+    const DevSource &source = sweep_source(P, s_sweep);
+    const DevReduce &red = sweep_reduce(P, s_sweep);
+    const long long row0 = SWEEP ? (long long)blockIdx.y * P.n_rays : 0;
+    const int k_red = reducing ? ((P.red.slab - 2) >> 1) : -1;      // the sample is the slab after surface k_red
+    const bool planes_in = (P.flags & RTB_FLAG_PLANES_IN) != 0, planes_out = (P.flags & RTB_FLAG_PLANES_OUT) != 0;
+    const long long out_rows = P.out_stride / 8;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned *const my_counts = PROBE ? probe_counts + (size_t)(SWEEP ? blockIdx.y : 0) * kMaxSurfaces * 2 : nullptr;
+
+    // warp-uniform trip count: every lane of a warp runs the same iterations, lanes past the end idle
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < P.n_rays; base += stride) {
+        long long i = base + threadIdx.x;
+        const bool valid = i < P.n_rays;
+        if (PROBE) {
+            // the probe's ray `i` of the sample is ray i * stride + jitter of the real launch (the jitter keeps the sample
+            // off the rows / columns of a Cartesian source)
+            const long long st = P.lean_probe_stride;
+            i = i * st + (long long)((unsigned)(i * 2654435761u) % (unsigned long long)st);
+            if (i >= P.lean_probe_total) i = P.lean_probe_total - 1;
+        }
+        Ray cur;
+        set_nan(cur);
+        if (valid) {
+            if (FROM_SOURCE)
+                cur = make_ray(source, source.first + i);
+            else
+                load_ray(P.rays_in, i, PROBE ? P.lean_probe_total : P.n_rays, planes_in, cur);
+        }
+        const double wl0 = cur.wl;
+        const double wl_rcp = xm::refine_rcp(wl0);
+        int row = 0;
+        bool listed = true;
+        if (USE_TABLE) {
+            row = P.n_wl;
+            const long long bits = __double_as_longlong(wl0);
+#pragma unroll 1
+            for (int k = 0; k < P.n_wl; k++)
+                if (__double_as_longlong(P.wl[k]) == bits) row = k;
+            listed = row != P.n_wl;              // NaN and unlisted wavelengths take the careful route
+        }
+        const double *pair = s_pair + 2 * row * n_med;
+        // The lean and optimistic steps assume finite geometry and a wavelength in [2^-100, 2^100] (then no phase
+        // quotient can leave the normal range); anything else is the careful route's business.
+        auto non_finite = [](double v) { return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000; };
+        const unsigned wl_exp = ((unsigned)__double2hiint(wl0) >> 20) & 0x7ffu;
+        const bool fit = valid && listed && (wl_exp - 923u <= 200u) &&
+                         !(non_finite(cur.ox) | non_finite(cur.oy) | non_finite(cur.oz) | non_finite(cur.dx) |
+                           non_finite(cur.dy) | non_finite(cur.dz) | non_finite(cur.ph));
+        bool failed = valid && !fit;             // to be re-traced by redo_ray
+        bool alive = fit;
+        bool sampled = false;
+        lean::State r = {cur.ox, cur.oy, cur.oz, cur.dx, cur.dy, cur.dz, cur.ph};
+        double n1 = 0.0;
+        if (!USE_TABLE) n1 = eval_index(P.mat[0], wl0);
+
+        if (!PROBE) {
+            // ---- the hot loop: warp-convergent from top to bottom.  Every lane runs every surface -- a dead or failed
+            // ray's lane computes on with whatever it holds (nothing it computes is used; it has no side effects) -- so
+            // the loop index is warp-uniform where the compiler can see it and the prescription is read through the
+            // uniform datapath / constant bank instead of vector registers.  Whole warps of dead rays leave early.
+            for (int k = 0; k < P.n_surf; k++) {
+                if (!__any_sync(0xffffffffu, alive)) break;
+                const DevSurface &s = P.surf[k];
+                const SurfaceShared ss = s_c.surf[k];
+                const int code = ss.code;
+                double ratio, n2 = 0.0;
+                if (USE_TABLE) {
+                    n1 = pair[0];
+                    ratio = pair[1];
+                    if (code == kGeneralLens) n2 = pair[2];
+                    pair += 2;
+                } else {
+                    n2 = eval_index(P.mat[k + 1], wl0);
+                    ratio = xm::div(n1, n2);
+                }
+                bool ok = true, on;
+                if (code == kLeanSphere) {
+                    on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp);
+                } else if (code == kLeanFlat) {
+                    on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp);
+                } else {
+                    on = general_step(s, code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok);
+                }
+                failed = failed || (alive && !ok);
+                alive = alive && ok && on;
+                if (!USE_TABLE) n1 = n2;
+                if (k == k_red && alive) {
+                    accumulate(red, r.ox, r.oy, r.oz, r.ph, s_tally);
+                    sampled = true;
+                }
+            }
+        } else {
+            // ---- the probe: per-surface recovery, so that every surface is probed with the rays that really reach it
+            for (int k = 0; k < P.n_surf; k++) {
+                if (!alive) break;
+                const DevSurface &s = P.surf[k];
+                const SurfaceShared ss = s_c.surf[k];
+                const int code = ss.code;
+                double ratio, n2;
+                if (USE_TABLE) {
+                    n1 = pair[0];
+                    ratio = pair[1];
+                    n2 = pair[2];
+                    pair += 2;
+                } else {
+                    n2 = eval_index(P.mat[k + 1], wl0);
+                    ratio = xm::div(n1, n2);
+                }
+                const lean::State before = r;
+                bool ok = true, on;
+                if (code == kLeanSphere)
+                    on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp);
+                else if (code == kLeanFlat)
+                    on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp);
+                else
+                    on = general_step(s, code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok);
+                atomicAdd(my_counts + 2 * k, 1u);
+                if (!ok) {
+                    atomicAdd(my_counts + 2 * k + 1, 1u);
+                    Ray in;
+                    in.ox = before.ox; in.oy = before.oy; in.oz = before.oz;
+                    in.dx = before.dx; in.dy = before.dy; in.dz = before.dz;
+                    in.ph = before.ph; in.wl = wl0;
+                    StepResult res;
+                    if (s.kind == RTB_SURF_FLAT || s.kind == RTB_SURF_SPHERE)
+                        res = careful_refracting(&s, in, n1, ratio, true);
+                    else if (s.kind == RTB_SURF_MIRROR)
+                        res = careful_mirror(&s, in, n1);
+                    else
+                        res = careful_lens(&s, in, n1, n2, false);
+                    r.ox = res.after.ox; r.oy = res.after.oy; r.oz = res.after.oz;
+                    r.dx = res.after.dx; r.dy = res.after.dy; r.dz = res.after.dz;
+                    r.ph = res.after.ph;
+                    on = !res.dead;
+                }
+                alive = on;
+                if (!USE_TABLE) n1 = n2;
+            }
+        }
+        if (PROBE) continue;
+
+        Ray out;
+        out.ox = r.ox; out.oy = r.oy; out.oz = r.oz; out.dx = r.dx; out.dy = r.dy; out.dz = r.dz; out.ph = r.ph;
+        out.wl = wl0;
+        if (!alive) set_nan(out);
+        if (failed) {
+            // start over from the launch state (reloaded: it was not kept in registers)
+            Ray launch, sample;
+            if (FROM_SOURCE)
+                launch = make_ray(source, source.first + i);
+            else
+                load_ray(P.rays_in, i, P.n_rays, planes_in, launch);
+            redo_ray<USE_TABLE>(&P, launch, k_red, &out, &sample);
+            if (reducing && !sampled) accumulate(red, sample.ox, sample.oy, sample.oz, sample.ph, s_tally);
+        }
+        if (valid && P.any_store) store_ray(P.out, row0 + i, out_rows, planes_out, out);
+    }
+    if (reducing) flush_tally(red, s_tally);
+}
+
+template <bool T, bool S, bool W, bool PR>
+cudaError_t launch_lean_one(const TraceParams &P, unsigned blocks, unsigned n_y, unsigned *probe_counts, cudaStream_t stream)
+{
+    size_t dyn = T ? 2 * sizeof(double) * (size_t)(P.n_wl + 1) * (size_t)(P.n_surf + 1) : 0;
+    if (!PR && P.red.slab >= 0 && P.red.stats) dyn += sizeof(double) * 12 * kLeanThreads;
+    trace_lean_kernel<T, S, W, PR><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
+    return cudaGetLastError();
+}
+
+template <bool PR>
+cudaError_t launch_lean_pick(const TraceParams &P, unsigned blocks, unsigned *probe_counts, cudaStream_t stream)
+{
+    const bool table = P.n_wl > 0, source = P.src.kind >= 0, sweep = P.n_src > 0;
+    const unsigned n_y = sweep ? (unsigned)P.n_src : 1u;
+    if (sweep)
+        return table ? launch_lean_one<true, true, true, PR>(P, blocks, n_y, probe_counts, stream)
+                     : launch_lean_one<false, true, true, PR>(P, blocks, n_y, probe_counts, stream);
+    if (table)
+        return source ? launch_lean_one<true, true, false, PR>(P, blocks, 1, probe_counts, stream)
+                      : launch_lean_one<true, false, false, PR>(P, blocks, 1, probe_counts, stream);
+    return source ? launch_lean_one<false, true, false, PR>(P, blocks, 1, probe_counts, stream)
+                  : launch_lean_one<false, false, false, PR>(P, blocks, 1, probe_counts, stream);
+}
+
+} // namespace
+
+// What the lean kernel traces: fp64 exact, nothing stored but the final slab (or nothing at all), no reduction or one at
+// an after-surface slab, not the intersect-only operator.
+bool lean_eligible(const TraceParams &P)
+{
+    if (P.flags & RTB_FLAG_INTERSECT_ONLY) return false;
+    if (P.any_store && !P.store_last_only) return false;
+    if (P.red.slab >= 0 && (P.red.slab < 2 || (P.red.slab & 1) != 0)) return false;
+    if (P.red.slab < 0 && !P.any_store) return false;      // nothing to do: leave it to the general kernel's conventions
+    return P.n_surf > 0;
+}
+
+// `counts`: device scratch of n_sources * kMaxSurfaces * 2 unsigned for the probe (zeroed here), owned by the caller for
+// the duration of both launches.  *launches is increased by the number of kernels launched.
+cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_count, cudaStream_t stream, int *launches)
+{
+    if (P_in.n_rays <= 0) return cudaSuccess;
+    TraceParams P = P_in;
+    const bool sweep = P.n_src > 0;
+    const int n_sources = sweep ? P.n_src : 1;
+    // surfaces without a lean step (tilted / decentred axes, mirrors, lenses) run the general steps
+    P.lean_general = 0ull;
+    for (int k = 0; k < P.n_surf; k++) {
+        const DevSurface &s = P.surf[k];
+        const bool lean_kind = (s.kind == RTB_SURF_SPHERE && s.z_axis != 0) ||
+                               (s.kind == RTB_SURF_FLAT && s.z_axis != 0 && s.z_normal != 0);
+        if (!lean_kind) P.lean_general |= 1ull << k;
+    }
+    cudaError_t e;
+    P.lean_counts = nullptr;
+    if (counts) {
+        e = cudaMemsetAsync(counts, 0, sizeof(unsigned) * 2 * kMaxSurfaces * (size_t)n_sources, stream);
+        if (e != cudaSuccess) return e;
+        TraceParams Q = P;
+        const long long n_probe = P.n_rays < kProbeRays ? P.n_rays : kProbeRays;
+        Q.lean_probe_total = P.n_rays;
+        Q.lean_probe_stride = P.n_rays / n_probe;
+        Q.n_rays = n_probe;
+        Q.red.slab = -1;
+        Q.any_store = 0;
+        const unsigned pb = (unsigned)((n_probe + kLeanThreads - 1) / kLeanThreads);
+        e = launch_lean_pick<true>(Q, pb, counts, stream);
+        if (e != cudaSuccess) return e;
+        if (launches) ++*launches;
+        P.lean_counts = counts;
+    }
+    long long blocks = (P.n_rays + kLeanThreads - 1) / kLeanThreads;
+    long long max_blocks = (long long)sm_count * kLeanMinBlocks * 4;
+    if (sweep) max_blocks = (max_blocks + P.n_src - 1) / P.n_src;
+    if (blocks > max_blocks) blocks = max_blocks;
+    e = launch_lean_pick<false>(P, (unsigned)blocks, nullptr, stream);
+    if (e == cudaSuccess && launches) ++*launches;
+    return e;
+}
+
+} // namespace rtb
