@@ -231,10 +231,15 @@ int64_t rtb_launch_count(void);
  *   "lean_min_rays"  launches of at least this many rays that keep only the final slab and / or one after-surface
  *                    reduction run the probe + lean kernel pair (csrc/trace_lean.cu); default 32768, negative = never.
  *                    The environment variable RTB_LEAN_MIN_RAYS sets the initial value.
+ *   "keep_probe_counts" test hook: 1 = every lean launch synchronises and keeps its probe's per-surface counts for
+ *                    rtb_last_probe_counts().
  *   "host_fail_chunk" test hook: rtb_trace_host returns RTB_ERR_CUDA when it is about to launch chunk n (0-based) of a
  *                    call (negative = off), after draining every copy already in flight.
  */
 int rtb_tune(const char *key, int64_t value);
+/* out[2k] = probe rays that reached surface k, out[2k+1] = those whose lean step failed there (last lean launch made
+   with "keep_probe_counts" on; first source of a sweep) */
+int rtb_last_probe_counts(uint32_t *out, int n_surfaces);
 
 /* ---- the hot path: replaces System.ray_trace, raytrace.py:641-661 --------------------------------------- */
 /*

@@ -88,7 +88,7 @@ EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_
            "rtb_trace_host", "rtb_trace_source", "rtb_trace_sources", "rtb_generate_device", "rtb_reduce_init",
            "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_dfma_chain_rate",
            "rtb_measure_copy_bandwidth", "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
-           "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device", "rtb_tune"]
+           "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device", "rtb_tune", "rtb_last_probe_counts"]
 
 
 def lib():
@@ -127,6 +127,8 @@ def lib():
     L.rtb_measure_dfma_rate.argtypes = [i32, dp, dp]
     L.rtb_measure_dfma_chain_rate.argtypes = [i32, i32, dp, dp]
     L.rtb_measure_copy_bandwidth.argtypes = [i32, i64, dp]
+    L.rtb_last_probe_counts.argtypes = [C.POINTER(C.c_uint32), i32]
+    L.rtb_last_probe_counts.restype = i32
     L.rtb_tune.argtypes = [C.c_char_p, i64]
     L.rtb_tune.restype = i32
     L.rtb_host_alloc.argtypes = [C.c_size_t]

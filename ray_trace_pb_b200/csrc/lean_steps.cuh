@@ -13,7 +13,7 @@
 //   * turn +-1 multiplications and np.sign selects into one integer operation on the sign bit,
 //   * pick the sphere's root before it is computed (one subtraction instead of two roots and two selects),
 //   * collect every domain test into one predicate with chained compares, and carry NO in-line handling of exact
-//     zeros: a ray whose flag comes back false is re-traced from its launch state by the careful per-surface
+//     zeros but one (the z component of d x n at a sphere, see unit3_zero_z): a ray whose flag comes back false is re-traced from its launch state by the careful per-surface
 //     machinery of surface_steps.cuh (trace_lean.cu: redo_ray), and surfaces where whole bundles produce zeros are
 //     found by a probe launch and run the zero-tolerant steps of surface_steps.cuh instead (policy mask).
 // A true flag means every intermediate was an ordinary normal number, so every rounding below is the one the
@@ -66,6 +66,22 @@ __device__ __forceinline__ void unit3(bool &ok, double &x, double &y, double &z,
     z = xm::div_core(z, l, r);
 }
 
+// The same for d x n at a sphere on the z axis, whose z component may be an exact zero.  For a ray in a plane through the
+// lens axis -- every ray of a beam parallel to the axis, at every surface of a coaxial train -- dx ny - dy nx vanishes
+// mathematically, and in floating point it is rounding noise that comes out exactly zero for a good part of the rays;
+// for a beam along z itself it is (+-0) ny - (+-0) nx.  (+-0) / l = +-0: the fast quotient gives +0 for both, so the sign
+// bit of the numerator is copied onto it (a no-op for a non-zero numerator: l > 0).
+__device__ __forceinline__ void unit3_zero_z(bool &ok, double &x, double &y, double &z, double l)
+{
+    const double r = xm::refine_rcp(l);
+    const bool z_is_zero = ((__double2hiint(z) & 0x7fffffff) | __double2loint(z)) == 0;
+    ok &= xm::num_ok(x) & xm::num_ok(y) & (xm::num_ok(z) | z_is_zero);
+    x = xm::div_core(x, l, r);
+    y = xm::div_core(y, l, r);
+    const double q = xm::div_core(z, l, r);
+    z = __hiloint2double(__double2hiint(q) | (__double2hiint(z) & (int)0x80000000), __double2loint(q));
+}
+
 __device__ __forceinline__ void unit2(bool &ok, double &x, double &y, double l)
 {
     const double r = xm::refine_rcp(l);
@@ -109,7 +125,7 @@ __device__ __forceinline__ bool sphere_axial(bool &ok, const DevSurface &s, doub
     double bx = r.dy * nz - r.dz * ny;
     double by = r.dz * nx - r.dx * nz;
     double bz = r.dx * ny - r.dy * nx;
-    unit3(ok, bx, by, bz, sqrt_unit_chk(ok, sumsq3(bx, by, bz)));
+    unit3_zero_z(ok, bx, by, bz, sqrt_unit_chk(ok, sumsq3(bx, by, bz)));
     double cx = ny * bz - nz * by;
     double cy = nz * bx - nx * bz;
     double cz = nx * by - ny * bx;

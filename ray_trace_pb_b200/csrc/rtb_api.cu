@@ -46,6 +46,10 @@ std::atomic<long long> g_lean_min_rays{32768};
 // test hook: rtb_trace_host fails (RTB_ERR_CUDA, "injected") when it is about to launch chunk number n (0-based) of a
 // call; negative = off.  rtb_tune("host_fail_chunk", n).  Lets the tests check that an error return leaves no copy in flight.
 std::atomic<long long> g_host_fail_chunk{-1};
+// test hook: rtb_tune("keep_probe_counts", 1) makes every lean launch synchronise and keep its probe's counts (first
+// source only) for rtb_last_probe_counts()
+std::atomic<long long> g_keep_probe_counts{0};
+unsigned g_last_probe_counts[2 * RTB_MAX_SURFACES];
 
 int fail(int code, const char *fmt, ...)
 {
@@ -400,6 +404,9 @@ int launch(const rtb::TraceParams &P, int precision, DeviceCtx *ctx, int device,
         }
         int launches = 0;
         cudaError_t e = rtb::launch_trace_lean(P, counts, ctx->sm_count, stream, &launches);
+        if (e == cudaSuccess && g_keep_probe_counts.load(std::memory_order_relaxed))
+            e = cudaMemcpyAsync(g_last_probe_counts, counts, sizeof(g_last_probe_counts), cudaMemcpyDeviceToHost, stream),
+            cudaStreamSynchronize(stream);
         if (!lean_counts) cudaFreeAsync(counts, stream);
         if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString(e));
         g_launches.fetch_add(launches, std::memory_order_relaxed);
@@ -466,11 +473,22 @@ int rtb_device_count(void)
 
 int64_t rtb_launch_count(void) { return g_launches.load(); }
 
+int rtb_last_probe_counts(uint32_t *out, int n_surfaces)
+{
+    if (!out || n_surfaces < 0 || n_surfaces > RTB_MAX_SURFACES) return fail(RTB_ERR_INVALID, "bad arguments");
+    for (int k = 0; k < 2 * n_surfaces; k++) out[k] = g_last_probe_counts[k];
+    return RTB_OK;
+}
+
 int rtb_tune(const char *key, int64_t value)
 {
     if (!key) return fail(RTB_ERR_INVALID, "key is NULL");
     if (strcmp(key, "lean_min_rays") == 0) {
         g_lean_min_rays.store(value, std::memory_order_relaxed);
+        return RTB_OK;
+    }
+    if (strcmp(key, "keep_probe_counts") == 0) {
+        g_keep_probe_counts.store(value, std::memory_order_relaxed);
         return RTB_OK;
     }
     if (strcmp(key, "host_fail_chunk") == 0) {
