@@ -92,9 +92,10 @@ __device__ __forceinline__ void unit2(bool &ok, double &x, double &y, double l)
 
 // SphericalSurface through RefractingSurface.propagate, input axis (0, 0, +-1).  `wl`, `wl_rcp`: the launch wavelength
 // (2^-100 <= |wl| <= 2^100, checked once per ray) and its refined reciprocal; `r_rcp`: refined 1/R, usable (checked per
-// block).  Returns "alive": on the sphere inside the aperture and not culled.  Updates the ray in place.
+// block).  Returns "alive": on the sphere inside the aperture and not culled; `kill`: the at-surface slab's row is blank
+// (raytrace.py:1187-1192; position and phase of that slab are the ones left in `r`).  Updates the ray in place.
 __device__ __forceinline__ bool sphere_axial(bool &ok, const DevSurface &s, double r_rcp, State &r, double n1, double ratio,
-                                             double wl, double wl_rcp)
+                                             double wl, double wl_rcp, bool &kill)
 {
     // get_intersect (raytrace.py:1479-1516)
     const double qx = r.ox - s.cx, qy = r.oy - s.cy, qz = r.oz - s.cz;
@@ -119,8 +120,8 @@ __device__ __forceinline__ bool sphere_axial(bool &ok, const DevSurface &s, doub
     const double s_on = sumsq3(rx, ry, rz);
     const double s_ap = px * px + py * py;
     // (bitwise, not short-circuit: four chained compares instead of branches around them)
-    const bool on = (s_on >= s.on_sq_lo) & (s_on <= s.on_sq_hi) & (s_ap <= s.ap_sq_max) &
-                    !(r.dz * s.az < 0.0);                  // front-side cull, raytrace.py:1187-1192
+    kill = r.dz * s.az < 0.0;                              // front-side cull, raytrace.py:1187-1192
+    const bool on = (s_on >= s.on_sq_lo) & (s_on <= s.on_sq_hi) & (s_ap <= s.ap_sq_max) & !kill;
     // Snell (raytrace.py:1197-1216)
     double bx = r.dy * nz - r.dz * ny;
     double by = r.dz * nx - r.dx * nz;
@@ -151,7 +152,7 @@ __device__ __forceinline__ bool sphere_axial(bool &ok, const DevSurface &s, doub
 // The signs of the exact zeros never reach a result.  A ray along the normal (d x n = 0), one that starts on the plane
 // (t = +-0) or lies in the x = 0 / y = 0 plane fails the flag.
 __device__ __forceinline__ bool flat_axial(bool &ok, const DevSurface &s, State &r, double n1, double ratio, double wl,
-                                           double wl_rcp)
+                                           double wl_rcp, bool &kill)
 {
     // propagate_ray2plane (raytrace.py:241-306) with exclude_backward_propagation (303-304)
     const double num = (r.oz - s.cz) * s.nz;
@@ -165,8 +166,8 @@ __device__ __forceinline__ bool flat_axial(bool &ok, const DevSurface &s, State 
     r.ph = r.ph + xm::div_core(len * kTwoPi, wl, wl_rcp) * n1;
     // is_pt_on_surface (raytrace.py:1339-1347), front-side cull (1187-1192)
     const double rx = px - s.cx, ry = py - s.cy, rz = pz - s.cz;
-    const bool on = !(t < 0.0) & (fabs(rz * s.nz) < kOnSurfaceTol) & (sumsq3(rx, ry, rz) <= s.ap_sq_max) &
-                    !(r.dz * s.az < 0.0);
+    kill = (t < 0.0) | (r.dz * s.az < 0.0);
+    const bool on = !kill & (fabs(rz * s.nz) < kOnSurfaceTol) & (sumsq3(rx, ry, rz) <= s.ap_sq_max);
     // Snell in the plane
     double bx = r.dy * s.nz, by = -(r.dx * s.nz);
     unit2(ok, bx, by, sqrt_unit_chk(ok, bx * bx + by * by));

@@ -117,6 +117,12 @@ struct TraceParams {
     unsigned long long lean_general;
     long long lean_probe_stride;
     long long lean_probe_total;
+    // runs of consecutive surfaces that take the same step (StepCode in trace_lean.cu), decided by the launcher: the
+    // hot loops' control flow depends on kernel parameters only, which keeps their index in a uniform register
+    int32_t lean_n_runs;
+    int32_t lean_sample_run;         // the reduction samples after this run (-1: no reduction)
+    uint8_t lean_run_end[kMaxSurfaces + 2];
+    uint8_t lean_run_code[kMaxSurfaces + 2];
     DevSurface surf[kMaxSurfaces];
     DevMaterial mat[kMaxMedia];
     double wl[kMaxWavelengths];

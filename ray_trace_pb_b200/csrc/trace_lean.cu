@@ -53,12 +53,15 @@ struct __align__(16) SurfaceShared {
 
 struct LeanShared {
     SurfaceShared surf[kMaxSurfaces];
+    int run_clean[kMaxSurfaces + 2];      // the probe overrode no surface of this run (see TraceParams::lean_run_*)
 };
 
 // ---- the careful whole-ray trace: a ray whose lean flag failed starts over here --------------------------------------
-// Returns the final slab's row (blanked when the ray is dead) and the row of slab 2 * k_sample + 2.
+// Returns the final slab's row (blanked when the ray is dead) and the row of slab 2 * k_sample + 2 (or, sample_at,
+// 2 * k_sample + 1).
 template <bool USE_TABLE>
-static __device__ __noinline__ void redo_ray(const TraceParams *P, Ray cur, int k_sample, Ray *final_row, Ray *sample_row)
+static __device__ __noinline__ void redo_ray(const TraceParams *P, Ray cur, int k_sample, bool sample_at, Ray *final_row,
+                                             Ray *sample_row)
 {
     const int n_med = P->n_surf + 1;
     const double wl0 = cur.wl;
@@ -94,11 +97,12 @@ static __device__ __noinline__ void redo_ray(const TraceParams *P, Ray cur, int 
             } else {
                 res = careful_lens(s, cur, n1, n2, false);
             }
+            if (k == k_sample && sample_at) *sample_row = res.at;
             cur = res.after;
             dead = res.dead;
             n1 = n2;
         }
-        if (k == k_sample) *sample_row = dead ? blank : cur;
+        if (k == k_sample && !sample_at) *sample_row = dead ? blank : cur;
     }
     *final_row = dead ? blank : cur;
 }
@@ -173,7 +177,7 @@ __device__ __noinline__ void flush_tally(const DevReduce &R, const double *tally
 
 // the general steps of surface_steps.cuh with their zero forms in line, on the lean kernel's in-place state
 __device__ __forceinline__ bool general_step(const DevSurface &s, int code, double rcp_y, bool rcp_ok, lean::State &r, double n1,
-                                             double n2, double ratio, double wl0, double wl_rcp, bool &ok)
+                                             double n2, double ratio, double wl0, double wl_rcp, bool &ok, bool &kill)
 {
     OptimisticZ m;
     xm::Rcp rcp_wl, rcp_k;
@@ -187,12 +191,13 @@ __device__ __forceinline__ bool general_step(const DevSurface &s, int code, doub
     AtRaw raw;
     bool dead;
     if (code == kGeneralRefracting)
-        dead = refracting_step<OptimisticZ, false>(m, s, in, n1, ratio, rcp_wl, rcp_k, true, raw, after);
+        dead = refracting_step<OptimisticZ, true>(m, s, in, n1, ratio, rcp_wl, rcp_k, true, raw, after);
     else if (code == kGeneralMirror)
-        dead = mirror_step<OptimisticZ, false>(m, s, in, n1, rcp_wl, raw, after);
+        dead = mirror_step<OptimisticZ, true>(m, s, in, n1, rcp_wl, raw, after);
     else
         dead = perfect_lens_step<OptimisticZ>(m, s, in, n1, n2, rcp_wl, rcp_k, false, false, raw, after);
     ok = m.ok;
+    kill = raw.kill;       // (a perfect lens's "at" slab is not offered as a sample: lean_eligible)
     r.ox = after.ox; r.oy = after.oy; r.oz = after.oz;
     r.dx = after.dx; r.dy = after.dy; r.dz = after.dz;
     r.ph = after.ph;
@@ -246,11 +251,20 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
         s_c.surf[k].code = code;
     }
     __syncthreads();
+    for (int run = threadIdx.x; run < P.lean_n_runs; run += blockDim.x) {
+        bool clean = true;
+        for (int k = run > 0 ? P.lean_run_end[run - 1] : 0; k < P.lean_run_end[run]; k++)
+            clean &= s_c.surf[k].code == P.lean_run_code[run];
+        s_c.run_clean[run] = clean;
+    }
+    __syncthreads();
 
     const DevSource &source = sweep_source(P, s_sweep);
     const DevReduce &red = sweep_reduce(P, s_sweep);
     const long long row0 = SWEEP ? (long long)blockIdx.y * P.n_rays : 0;
-    const int k_red = reducing ? ((P.red.slab - 2) >> 1) : -1;      // the sample is the slab after surface k_red
+    // the sample is the slab after surface k_red (even slab) or at it (odd slab)
+    const int k_red = reducing ? ((P.red.slab - 1) >> 1) : -1;
+    const bool sample_at = reducing && (P.red.slab & 1) != 0;
     const bool planes_in = (P.flags & RTB_FLAG_PLANES_IN) != 0, planes_out = (P.flags & RTB_FLAG_PLANES_OUT) != 0;
     const long long out_rows = P.out_stride / 8;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -297,7 +311,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                            non_finite(cur.dy) | non_finite(cur.dz) | non_finite(cur.ph));
         bool failed = valid && !fit;             // to be re-traced by redo_ray
         bool alive = fit;
-        bool sampled = false;
+        bool sampled = false, at_valid = false;
         lean::State r = {cur.ox, cur.oy, cur.oz, cur.dx, cur.dy, cur.dz, cur.ph};
         double n1 = 0.0;
         if (!USE_TABLE) n1 = eval_index(P.mat[0], wl0);
@@ -307,33 +321,86 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
             // ray's lane computes on with whatever it holds (nothing it computes is used; it has no side effects) -- so
             // the loop index is warp-uniform where the compiler can see it and the prescription is read through the
             // uniform datapath / constant bank instead of vector registers.  Whole warps of dead rays leave early.
-            for (int k = 0; k < P.n_surf; k++) {
-                if (!__any_sync(0xffffffffu, alive)) break;
-                const DevSurface &s = P.surf[k];
-                const SurfaceShared ss = s_c.surf[k];
-                const int code = ss.code;
-                double ratio, n2 = 0.0;
-                if (USE_TABLE) {
-                    n1 = pair[0];
-                    ratio = pair[1];
-                    if (code == kGeneralLens) n2 = pair[2];
-                    pair += 2;
-                } else {
-                    n2 = eval_index(P.mat[k + 1], wl0);
-                    ratio = xm::div(n1, n2);
-                }
-                bool ok = true, on;
+            // (each run's loop has its own induction variable, defined from kernel parameters only: the general steps
+            // branch on values loaded through theirs, which makes it a vector register; the lean loops' stay uniform)
+            for (int run = 0; run < P.lean_n_runs; run++) {
+                const int begin = run > 0 ? P.lean_run_end[run - 1] : 0;
+                const int end = P.lean_run_end[run];
+                // (a run is "clean" when the probe left every surface of it on the launcher's step)
+                const int code = s_c.run_clean[run] ? P.lean_run_code[run] : kGeneralRefracting;
                 if (code == kLeanSphere) {
-                    on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp);
+                    for (int k = begin; k < end; k++) {
+                        if (!__any_sync(0xffffffffu, alive)) {
+                            at_valid = false;      // (the surface that would have been sampled is not reached)
+                            break;
+                        }
+                        if (USE_TABLE) {
+                            n1 = pair[0];
+                            pair += 2;
+                        }
+                        const double n2 = USE_TABLE ? 0.0 : eval_index(P.mat[k + 1], wl0);
+                        const double ratio = USE_TABLE ? pair[-1] : xm::div(n1, n2);
+                        bool ok = true, kill;
+                        const bool on = lean::sphere_axial(ok, P.surf[k], s_c.surf[k].rcp, r, n1, ratio, wl0, wl_rcp, kill);
+                        failed = failed | (alive & !ok);
+                        at_valid = alive & ok & !kill;
+                        alive = alive & ok & on;
+                        if (!USE_TABLE) n1 = n2;
+                    }
                 } else if (code == kLeanFlat) {
-                    on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp);
+                    for (int k = begin; k < end; k++) {
+                        if (!__any_sync(0xffffffffu, alive)) {
+                            at_valid = false;      // (the surface that would have been sampled is not reached)
+                            break;
+                        }
+                        if (USE_TABLE) {
+                            n1 = pair[0];
+                            pair += 2;
+                        }
+                        const double n2 = USE_TABLE ? 0.0 : eval_index(P.mat[k + 1], wl0);
+                        const double ratio = USE_TABLE ? pair[-1] : xm::div(n1, n2);
+                        bool ok = true, kill;
+                        const bool on = lean::flat_axial(ok, P.surf[k], r, n1, ratio, wl0, wl_rcp, kill);
+                        failed = failed | (alive & !ok);
+                        at_valid = alive & ok & !kill;
+                        alive = alive & ok & on;
+                        if (!USE_TABLE) n1 = n2;
+                    }
                 } else {
-                    on = general_step(s, code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok);
+                    for (int k = begin; k < end; k++) {
+                        if (!__any_sync(0xffffffffu, alive)) {
+                            at_valid = false;      // (the surface that would have been sampled is not reached)
+                            break;
+                        }
+                        const DevSurface &s = P.surf[k];
+                        const SurfaceShared ss = s_c.surf[k];
+                        double ratio, n2 = 0.0;
+                        if (USE_TABLE) {
+                            n1 = pair[0];
+                            ratio = pair[1];
+                            n2 = pair[2];
+                            pair += 2;
+                        } else {
+                            n2 = eval_index(P.mat[k + 1], wl0);
+                            ratio = xm::div(n1, n2);
+                        }
+                        bool ok = true, kill;
+                        bool on;
+                        if (ss.code == kLeanSphere)
+                            on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp, kill);
+                        else if (ss.code == kLeanFlat)
+                            on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
+                        else
+                            on = general_step(s, ss.code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok, kill);
+                        failed = failed | (alive & !ok);
+                        at_valid = alive & ok & !kill;
+                        alive = alive & ok & on;
+                        if (!USE_TABLE) n1 = n2;
+                    }
                 }
-                failed = failed || (alive && !ok);
-                alive = alive && ok && on;
-                if (!USE_TABLE) n1 = n2;
-                if (k == k_red && alive) {
+                // the sample: the slab after the run's last surface, or (odd slab) the one at it -- whose position and
+                // phase the step has left in the ray, valid unless the ray was culled there
+                if (run == P.lean_sample_run && (sample_at ? at_valid : alive)) {
                     accumulate(red, r.ox, r.oy, r.oz, r.ph, s_tally);
                     sampled = true;
                 }
@@ -356,13 +423,13 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                     ratio = xm::div(n1, n2);
                 }
                 const lean::State before = r;
-                bool ok = true, on;
+                bool ok = true, on, kill;
                 if (code == kLeanSphere)
-                    on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp);
+                    on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp, kill);
                 else if (code == kLeanFlat)
-                    on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp);
+                    on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
                 else
-                    on = general_step(s, code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok);
+                    on = general_step(s, code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok, kill);
                 atomicAdd(my_counts + 2 * k, 1u);
                 if (!ok) {
                     atomicAdd(my_counts + 2 * k + 1, 1u);
@@ -399,7 +466,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                 launch = make_ray(source, source.first + i);
             else
                 load_ray(P.rays_in, i, P.n_rays, planes_in, launch);
-            redo_ray<USE_TABLE>(&P, launch, k_red, &out, &sample);
+            redo_ray<USE_TABLE>(&P, launch, k_red, sample_at, &out, &sample);
             if (reducing && !sampled) accumulate(red, sample.ox, sample.oy, sample.oz, sample.ph, s_tally);
         }
         if (valid && P.any_store) store_ray(P.out, row0 + i, out_rows, planes_out, out);
@@ -421,6 +488,9 @@ cudaError_t launch_lean_pick(const TraceParams &P, unsigned blocks, unsigned *pr
 {
     const bool table = P.n_wl > 0, source = P.src.kind >= 0, sweep = P.n_src > 0;
     const unsigned n_y = sweep ? (unsigned)P.n_src : 1u;
+#ifdef RTB_LEAN_ONLY_ONE   // experiments: one instantiation, seconds to compile
+    return launch_lean_one<true, false, false, PR>(P, blocks, 1, probe_counts, stream);
+#endif
     if (sweep)
         return table ? launch_lean_one<true, true, true, PR>(P, blocks, n_y, probe_counts, stream)
                      : launch_lean_one<false, true, true, PR>(P, blocks, n_y, probe_counts, stream);
@@ -439,7 +509,18 @@ bool lean_eligible(const TraceParams &P)
 {
     if (P.flags & RTB_FLAG_INTERSECT_ONLY) return false;
     if (P.any_store && !P.store_last_only) return false;
-    if (P.red.slab >= 0 && (P.red.slab < 2 || (P.red.slab & 1) != 0)) return false;
+    if (P.red.slab == 0) return false;                       // the launch rays themselves: nothing to trace for
+    // (an odd slab is the one AT a surface: the steps leave its position and phase in the ray -- except a perfect lens,
+    // whose "at" slab is a fourth plane propagation)
+    if (P.red.slab > 0 && (P.red.slab & 1) != 0 && P.surf[(P.red.slab - 1) >> 1].kind == RTB_SURF_PERFECT_LENS) return false;
+    // worth it when most surfaces have a lean step (on-axis spheres and flats); trains of perfect lenses, mirrors and
+    // tilted surfaces stay with trace_f64.cu, whose loops are built around the general steps
+    int n_lean = 0;
+    for (int k = 0; k < P.n_surf; k++) {
+        const DevSurface &s = P.surf[k];
+        n_lean += (s.kind == RTB_SURF_SPHERE && s.z_axis != 0) || (s.kind == RTB_SURF_FLAT && s.z_axis != 0 && s.z_normal != 0);
+    }
+    if (4 * n_lean < 3 * P.n_surf) return false;
     if (P.red.slab < 0 && !P.any_store) return false;      // nothing to do: leave it to the general kernel's conventions
     return P.n_surf > 0;
 }
@@ -459,6 +540,30 @@ cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_
         const bool lean_kind = (s.kind == RTB_SURF_SPHERE && s.z_axis != 0) ||
                                (s.kind == RTB_SURF_FLAT && s.z_axis != 0 && s.z_normal != 0);
         if (!lean_kind) P.lean_general |= 1ull << k;
+    }
+    // runs of equal step codes, split where the reduction samples
+    {
+        const int k_red = P.red.slab >= 0 ? (P.red.slab - 1) >> 1 : -1;
+        P.lean_n_runs = 0;
+        P.lean_sample_run = -1;
+        int prev = -1;
+        for (int k = 0; k < P.n_surf; k++) {
+            const DevSurface &s = P.surf[k];
+            int code = (s.kind == RTB_SURF_MIRROR) ? kGeneralMirror : (s.kind == RTB_SURF_PERFECT_LENS) ? kGeneralLens
+                                                                                                         : kGeneralRefracting;
+            const bool sane = std::isfinite(s.radius) && fabs(s.radius) > 1e-150 && fabs(s.radius) < 4503599627370496.0;
+            if (!((P.lean_general >> k) & 1ull) && (s.kind != RTB_SURF_SPHERE || sane))
+                code = (s.kind == RTB_SURF_SPHERE) ? kLeanSphere : kLeanFlat;
+            if (code >= kGeneralRefracting) code = kGeneralRefracting;      // one run type for every general step
+            if (code != prev) P.lean_n_runs++;
+            P.lean_run_code[P.lean_n_runs - 1] = (uint8_t)code;
+            P.lean_run_end[P.lean_n_runs - 1] = (uint8_t)(k + 1);
+            prev = code;
+            if (k == k_red) {
+                P.lean_sample_run = P.lean_n_runs - 1;
+                prev = -1;
+            }
+        }
     }
     cudaError_t e;
     P.lean_counts = nullptr;
