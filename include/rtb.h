@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 3 /* 2: rtb_surface.hints (was reserved), rtb_measure_dfma_chain_rate; 3: rtb_tune */
+#define RTB_ABI_VERSION 4 /* 2: rtb_surface.hints, rtb_measure_dfma_chain_rate; 3: rtb_tune; 4: rtb_comm_* */
 /* per launch (the prescription travels in the kernel parameter block); the host layer chains longer systems */
 #define RTB_MAX_SURFACES 64
 #define RTB_MAX_WAVELENGTHS 8 /* rows of the host refractive-index table (one extra row answers NaN wavelengths) */
@@ -298,6 +298,31 @@ int64_t rtb_psf_scratch_doubles(int grid_n, int n_samples, int normalize_by_coun
 int rtb_psf_from_grid_device(const double *grid_dev, int grid_n, double grid_half_width, int n_samples, double df,
                              int normalize_by_count, double *scratch_dev, int64_t scratch_doubles, double *psf_out_dev,
                              double *field_re_dev, double *field_im_dev, int device, void *stream);
+
+/* ---- multi-GPU: the one exchange step of the path --------------------------------------------------
+ * Rays shard by contiguous index range over one process per GPU (the reference has no counterpart: its loop,
+ * raytrace.py:641-661, is single-process); the trace never communicates.  What is exchanged afterwards are the reduced
+ * products of rtb_reduce: the pupil grid (summed) and the statistics vectors (8 sums, 2 minima, 2 maxima per bucket).
+ * These entry points wrap NCCL (resolved at run time from libnccl.so.2; RTB_ERR_UNSUPPORTED when it is absent) so that
+ * a binder without PyTorch can do the reduction.  Bootstrapping: rank 0 calls rtb_comm_unique_id and hands the
+ * RTB_COMM_ID_BYTES bytes to every rank (MPI, a file, a socket ...); then every rank calls rtb_comm_init, which blocks
+ * until all n_ranks have joined.  The collectives enqueue on `stream` and return; every rank must call them in the same
+ * order.  One communicator per (process, device); not thread safe.
+ */
+#define RTB_COMM_ID_BYTES 128
+typedef struct rtb_comm rtb_comm;
+/* NCCL's version code (e.g. 22809) when the library could be loaded, 0 otherwise */
+int rtb_comm_available(void);
+int rtb_comm_unique_id(void *id_out, size_t id_bytes);
+int rtb_comm_init(rtb_comm **comm_out, int n_ranks, int rank, const void *unique_id, int device);
+/* number of ranks of the communicator (negative rtb_status on error) */
+int rtb_comm_size(const rtb_comm *comm);
+/* in-place sum over the ranks of n_doubles doubles: the (3, G, G) grid of rtb_reduce, all buckets at once */
+int rtb_comm_allreduce_grid(rtb_comm *comm, double *grid_dev, int64_t n_doubles, void *stream);
+/* in-place merge over the ranks of n_buckets statistics vectors (RTB_N_STATS doubles each): one all-gather and a
+   merge kernel; sums are accumulated in rank order, so the result is the same on every rank and run to run */
+int rtb_comm_allreduce_stats(rtb_comm *comm, double *stats_dev, int n_buckets, void *stream);
+int rtb_comm_destroy(rtb_comm *comm);
 
 /* ---- after the trace: replaces intersect_rays, raytrace.py:164-238 ----------------------------------------- */
 /* ray1_dev, ray2_dev : (N, 8) device; pts_out_dev : (N, 3) device. n1 or n2 may be 1 (broadcast). */

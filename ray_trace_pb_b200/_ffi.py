@@ -18,7 +18,8 @@ import os
 # RTB_LIBRARY_PATH selects another build of the same library (used to A/B kernel variants on the GPU box)
 LIB_PATH = Path(os.environ.get("RTB_LIBRARY_PATH") or (Path(__file__).resolve().parent / "_lib" / "librtb.so"))
 
-RTB_ABI_VERSION = 3
+RTB_ABI_VERSION = 4
+RTB_COMM_ID_BYTES = 128
 RTB_MAX_SURFACES = 64
 RTB_MAX_WAVELENGTHS = 8
 RTB_N_STATS = 12
@@ -88,7 +89,9 @@ EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_
            "rtb_trace_host", "rtb_trace_source", "rtb_trace_sources", "rtb_generate_device", "rtb_reduce_init",
            "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_dfma_chain_rate",
            "rtb_measure_copy_bandwidth", "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
-           "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device", "rtb_tune", "rtb_last_probe_counts"]
+           "rtb_selftest_exact_math", "rtb_psf_scratch_doubles", "rtb_psf_from_grid_device", "rtb_tune", "rtb_last_probe_counts",
+           "rtb_comm_available", "rtb_comm_unique_id", "rtb_comm_init", "rtb_comm_size", "rtb_comm_allreduce_grid",
+           "rtb_comm_allreduce_stats", "rtb_comm_destroy"]
 
 
 def lib():
@@ -129,6 +132,19 @@ def lib():
     L.rtb_measure_copy_bandwidth.argtypes = [i32, i64, dp]
     L.rtb_last_probe_counts.argtypes = [C.POINTER(C.c_uint32), i32]
     L.rtb_last_probe_counts.restype = i32
+    L.rtb_comm_available.restype = i32
+    L.rtb_comm_unique_id.argtypes = [vp, C.c_size_t]
+    L.rtb_comm_unique_id.restype = i32
+    L.rtb_comm_init.argtypes = [C.POINTER(vp), i32, i32, vp, i32]
+    L.rtb_comm_init.restype = i32
+    L.rtb_comm_size.argtypes = [vp]
+    L.rtb_comm_size.restype = i32
+    L.rtb_comm_allreduce_grid.argtypes = [vp, vp, i64, vp]
+    L.rtb_comm_allreduce_grid.restype = i32
+    L.rtb_comm_allreduce_stats.argtypes = [vp, vp, i32, vp]
+    L.rtb_comm_allreduce_stats.restype = i32
+    L.rtb_comm_destroy.argtypes = [vp]
+    L.rtb_comm_destroy.restype = i32
     L.rtb_tune.argtypes = [C.c_char_p, i64]
     L.rtb_tune.restype = i32
     L.rtb_host_alloc.argtypes = [C.c_size_t]

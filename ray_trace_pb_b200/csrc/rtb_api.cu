@@ -60,6 +60,22 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
+} // namespace
+
+namespace rtb {
+// the same for the other translation units of the C ABI (comm.cu)
+int api_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+} // namespace rtb
+
+namespace {
+
 #define RTB_CUDA(call)                                                                                     \
     do {                                                                                                   \
         cudaError_t e_ = (call);                                                                           \

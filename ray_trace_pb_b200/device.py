@@ -409,7 +409,20 @@ class Reducer:
                 one.grid_dev = self.grid_t.data_ptr() + b * 3 * self.grid_n * self.grid_n * 8
             _ffi.check(_ffi.lib().rtb_reduce_init(C.byref(one), self.device, _stream_ptr(self.device)))
 
-    def allreduce(self):
+    def allreduce(self, comm=None):
+        """
+        Sum the grid and merge the statistics over the ranks, in place, enqueued on the current stream.  ``comm``: a
+        :class:`ray_trace_pb_b200.sharding.Comm` (the library's own NCCL communicator behind the C ABI: one all-reduce
+        for the grid, one all-gather + merge kernel for the statistics); without it the default torch.distributed
+        process group is used (any backend -- the CPU tests run this route over gloo).
+        """
+        if comm is not None:
+            stream = _stream_ptr(self.device)
+            if self.grid_t is not None:
+                comm.allreduce_grid(self.grid_t, stream)
+            if self.stats_t is not None:
+                comm.allreduce_stats(self.stats_t, stream)
+            return self
         from .sharding import allreduce_grid, allreduce_stats
         if self.grid_t is not None:
             allreduce_grid(self.grid_t)

@@ -84,6 +84,66 @@ def allreduce_grid(grid, dist=None):
     return grid
 
 
+class Comm:
+    """
+    The library's own communicator (rtb_comm_* in include/rtb.h: NCCL behind the C ABI, no torch types): what a binder
+    without PyTorch would use, and what ``Reducer.allreduce(comm=...)`` uses here.  Two collectives per exchange: one
+    all-reduce for the grid, one all-gather + merge kernel for the statistics of every bucket.
+    """
+
+    def __init__(self, n_ranks: int, rank: int, unique_id: bytes, device: int):
+        import ctypes as C
+        from . import _ffi
+        if len(unique_id) != _ffi.RTB_COMM_ID_BYTES:
+            raise ValueError(f"unique_id must be {_ffi.RTB_COMM_ID_BYTES} bytes")
+        self._lib = _ffi.lib()
+        self._handle = C.c_void_p()
+        self.n_ranks, self.rank, self.device = n_ranks, rank, device
+        _ffi.check(self._lib.rtb_comm_init(C.byref(self._handle), n_ranks, rank, unique_id, device))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _ffi
+        buf = C.create_string_buffer(_ffi.RTB_COMM_ID_BYTES)
+        _ffi.check(_ffi.lib().rtb_comm_unique_id(buf, _ffi.RTB_COMM_ID_BYTES))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: int):
+        """bootstrap over an initialised torch.distributed process group (any backend): rank 0's id is broadcast"""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        on_gpu = dist.get_backend() == "nccl"
+        buf = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}" if on_gpu else "cpu")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        return cls(world, rank, bytes(buf.cpu().numpy().tobytes()), device)
+
+    def size(self) -> int:
+        from . import _ffi
+        n = self._lib.rtb_comm_size(self._handle)
+        if n < 0:
+            _ffi.check(n)
+        return n
+
+    def allreduce_grid(self, grid, stream_ptr: int):
+        from . import _ffi
+        _ffi.check(self._lib.rtb_comm_allreduce_grid(self._handle, grid.data_ptr(), grid.numel(), stream_ptr))
+
+    def allreduce_stats(self, stats, stream_ptr: int):
+        from . import _ffi
+        n_buckets = stats.numel() // _ffi.RTB_N_STATS
+        _ffi.check(self._lib.rtb_comm_allreduce_stats(self._handle, stats.data_ptr(), n_buckets, stream_ptr))
+
+    def close(self):
+        if self._handle:
+            self._lib.rtb_comm_destroy(self._handle)
+            self._handle = None
+
+
 def merge_stats_host(parts) -> np.ndarray:
     """NumPy version of the same merge (used to check the collective path)."""
     parts = np.asarray(parts, dtype=np.float64)
