@@ -91,8 +91,134 @@ def link_probe(torch, device: int, nbytes: int = 1 << 28):
             t = min(t, time.perf_counter() - t0)
         return moved / t / 1e9
 
-    return {"h2d_gbps": best(h2d, nbytes), "d2h_gbps": best(d2h, nbytes),
-            "both_gbps": best(lambda: (h2d(), d2h()), 2 * nbytes)}
+    out = {"h2d_gbps": best(h2d, nbytes), "d2h_gbps": best(d2h, nbytes),
+           "both_gbps": best(lambda: (h2d(), d2h()), 2 * nbytes)}
+    out["_both"] = lambda: (h2d(), d2h())          # (for the all-ranks-at-once measurement; removed by the caller)
+    out["_bytes"] = 2 * nbytes
+    return out
+
+
+def link_probe_concurrent(torch, dist, probe, world: int, device: int):
+    """Every rank copies both ways AT THE SAME TIME (barrier, 3 back-to-back rounds, barrier): the box's aggregate
+    host<->device ceiling, which is what the N-GPU host-buffer path competes for."""
+    fn, moved = probe.pop("_both"), probe.pop("_bytes")
+    if world == 1:
+        probe["aggregate_gbps"] = probe["both_gbps"]
+        return probe
+    rounds = 3
+    fn()
+    torch.cuda.synchronize(device)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        fn()
+    torch.cuda.synchronize(device)
+    mine = rounds * moved / (time.perf_counter() - t0) / 1e9
+    t = torch.tensor([mine], dtype=torch.float64, device=f"cuda:{device}")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    probe["aggregate_gbps"] = float(t[0])
+    probe["concurrent_gbps_this_rank"] = mine
+    return probe
+
+
+# SURVEY.md 8d: algorithmic FP64-pipe instructions per surface kind (+ one dispersion evaluation of the new medium)
+I_ALG_KIND = {"SphericalSurface": 268.0, "FlatSurface": 210.0, "PlaneMirror": 185.0, "PerfectLens": 330.0}
+I_ALG_DISPERSION = 42.0
+
+
+def algorithmic_instr_per_ray(system, final_material):
+    """I_alg of SURVEY.md 8d for any system: per-kind step costs plus 42 per surface whose new medium is dispersive."""
+    total = 0.0
+    media = list(system.materials) + [final_material]
+    for surf, medium in zip(system.surfaces, media):
+        kind = next(k.__name__ for k in type(surf).__mro__ if k.__name__ in I_ALG_KIND)
+        total += I_ALG_KIND[kind]
+        if type(medium).__name__ not in ("Vacuum", "Constant"):
+            total += I_ALG_DISPERSION
+    return total
+
+
+def config_block(torch, dfma_rate: float):
+    """BASELINE.json configs 1-5 at full size on this GPU, device part only, timed with CUDA events (best of 3 after a
+    warm-up): the systems of the reference's scripts with their own bundles, through the same public calls as
+    examples/run_configs.py.  `frac` = that system's own I_alg x rays/s / the measured DFMA rate."""
+    import systems
+    import ray_trace_pb_b200.materials as rtm
+    import ray_trace_pb_b200.raytrace as rt
+    from ray_trace_pb_b200 import analysis, device as dev
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best
+
+    vac = rtm.Vacuum()
+    out = {}
+
+    def entry(name, workload, system, m_out, n_rays, ms):
+        i_alg = algorithmic_instr_per_ray(system, m_out)
+        n_surf = len(system.surfaces)
+        rays_per_s = n_rays / (ms * 1e-3)
+        out[name] = {"workload": workload, "rays": int(n_rays), "surfaces": n_surf, "kernel_ms": ms,
+                     "value": rays_per_s * n_surf, "unit": "ray*surfaces/s",
+                     "roofline": {"bound": "fp64", "algorithmic_instr_per_ray": i_alg,
+                                  "achieved": i_alg * rays_per_s / 1e9, "peak": dfma_rate / 1e9,
+                                  "unit": "G FP64-pipe instr/s", "frac": i_alg * rays_per_s / dfma_rate}}
+
+    # config 1: scripts/2022_10_27_plano_convex_lens.py scaled up (1001 x 1000 collimated rays), final slab
+    system, m_in, m_out, _ = systems.plano_convex(rt, rtm)
+    mats = [m_in] + system.materials + [m_out]
+    src = dev.RaySource.collimated([0, 0, -5], 25.4, 1001, 0.5, nphis=1000)
+    ms = timed(lambda: dev.trace_source(system.surfaces, mats, src, keep="last"))
+    entry("config1", "plano-convex lens, 1001 x 1000 collimated rays generated on the device, final slab", system, m_out,
+          src.n_rays, ms)
+    # config 2: scripts/2022_08_04_ACT508-100-B.py:58-72, 3 wavelengths x 4096^2 grid, spot statistics at the d-line focus
+    doublet = rt.Doublet(rtm.Nlak22(), rtm.Nsf6ht(), radius_crown=65.8, radius_flint=-280.6, radius_interface=-56,
+                         thickness_crown=13.0, thickness_flint=2.0, aperture_radius=25.4, names="AC508-100-B")
+    wls = (0.7065, 0.855, 1.015)
+    focus_z = float(doublet.get_cardinal_points(0.855, vac, vac)[1][2])
+    system = rt.System([rt.FlatSurface([0, 0, -5.0], [0, 0, 1], 25.4)], []).concatenate(doublet, vac)
+    system = system.concatenate(rt.FlatSurface([0, 0, focus_z], [0, 0, 1], 25.4), vac)
+    sources = [dev.RaySource.grid([0, 0, -10.0], 10.0, 4096, w) for w in wls]
+    ms = timed(lambda: analysis.spot_statistics(system, vac, vac, sources, slab=-2))
+    entry("config2", "AC508-100-B doublet + 2 flats, 3 wavelengths x 4096^2 grid in one sweep launch, fused spot "
+          "statistics at the focal plane (includes the statistics' device->host read)", system, vac, 3 * sources[0].n_rays, ms)
+    # config 3: scripts/2022_08_24_relay_astigmatism.py, 32 field bundles x 2048^2
+    system = systems.relay10_system(rt, rtm)
+    thetas = np.linspace(0, np.pi / 180, 32)
+    sources = [dev.RaySource.grid([0, 0, 0], 12.0, 2048, WAVELENGTH, normal=(np.sin(t), 0, np.cos(t))) for t in thetas]
+    ms = timed(lambda: analysis.spot_statistics(system, vac, vac, sources, slab=-2))
+    entry("config3", "10-surface relay, 32 field bundles x 2048^2 rays in one sweep launch, fused spot statistics per "
+          "field (includes the statistics' device->host read)", system, vac, 32 * sources[0].n_rays, ms)
+    # config 4: scripts/2022_01_25_ray_trace_ideal_opm.py, 16001 x 16000 fan -> O3 pupil grid
+    system, m_in, m_out, alpha1, theta = systems.opm_system(rt, rtm)
+    src = dev.RaySource.fan([1e-3, 1e-3, 1e-3 * np.tan(theta)], alpha1, 16001, 532e-6, nphis=16000)
+    o3n = system.surfaces[8].normal
+    e2 = np.array([0.0, 1.0, 0.0])
+    e1 = np.cross(e2, o3n)
+    chief = system.ray_trace(rt.get_ray_fan([1e-3, 1e-3, 1e-3 * np.tan(theta)], 0.0, 1, 532e-6), m_in, m_out)
+    ms = timed(lambda: analysis.pupil_grid(system, m_in, m_out, src, slab=-5, origin=system.surfaces[8].center, e1=e1,
+                                           e2=e2, grid_n=GRID_N, half_width=3.2, phase_ref=float(chief[-5, 0, 6])), reps=2)
+    entry("config4", "ideal OPM (6 perfect lenses + 5 flats, one tilted), 16001 x 16000 ray fan generated on the device "
+          "-> 2048^2 pupil grid at O3", system, m_out, src.n_rays, ms)
+    # config 5 on the script's own system: scripts/2024_08_08_achromat_imaging.py, one GPU's share of 1e9 rays
+    system = systems.achromat_imaging_system(rt, rtm)
+    src = dev.RaySource.fan([2.0, 0, 0], 4 * np.pi / 180, 11181, 0.635, nphis=11180)
+    pupil = system.surfaces[4]
+    ms = timed(lambda: analysis.pupil_grid(system, vac, vac, src, slab=2 * 4 + 2, origin=pupil.center, e1=(1, 0, 0),
+                                           e2=(0, 1, 0), grid_n=GRID_N, half_width=8.0))
+    entry("config5_achromat", "9-surface achromat imaging system (two AC508-075-A-ML, Ebaf11 / Nsf11 tabulated on the "
+          "host), 1.25e8-ray fan generated on the device -> 2048^2 pupil grid at the stop", system, vac, src.n_rays, ms)
+    return out
 
 
 class ClockSampler:
@@ -245,6 +371,7 @@ def main():
     ap.add_argument("--e2e-rays", type=float, default=float(1 << 24))
     ap.add_argument("--reduce", default="grid", choices=["none", "stats", "grid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (BASELINE configs 1-5, N = 1)")
     ap.add_argument("--no-bind", action="store_true", help="do not pin each rank to its GPU's local CPUs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -276,19 +403,45 @@ def main():
     # ---- resident inputs / outputs ---------------------------------------------------------------------
     rays = source.generate(first=first, count=n_rays, device=local)         # this rank's (N, 8) shard in HBM
     out = torch.empty((1, n_rays, 8), dtype=torch.float64, device=f"cuda:{local}")
-    reducer = None
+    # Two reducers, used alternately: step i's grid / statistics are exchanged (NCCL, on a side stream) while step
+    # i+1 traces into the other one -- the exchange is the only communication of the job and nothing waits for it
+    # except the reset of the same reducer two steps later and the end of the timed region.
+    reducers = []
     if args.reduce != "none":
         # sample just after the second doublet (slab 12), where the relay's beam is collimated: the pupil
-        reducer = dev.Reducer(12, origin=(8.0, 0, 0), grid_n=GRID_N if args.reduce == "grid" else 0,
-                              half_width=8.0, device=local)
+        reducers = [dev.Reducer(12, origin=(8.0, 0, 0), grid_n=GRID_N if args.reduce == "grid" else 0,
+                                half_width=8.0, device=local) for _ in range(2 if world > 1 else 1)]
+    reducer = reducers[0] if reducers else None
+    comm = None
+    if world > 1 and reducers:
+        from ray_trace_pb_b200.sharding import Comm
+        comm = Comm.from_torch_distributed(local)          # the library's own communicator (rtb_comm_*, C ABI)
+    comm_stream = torch.cuda.Stream(local) if comm is not None else None
+    ev_traced = [torch.cuda.Event() for _ in reducers]
+    ev_reduced = [torch.cuda.Event() for _ in reducers]
 
-    def step():
-        if reducer is not None:
-            reducer.reset()
-        dev.trace_tensor(system.surfaces, materials, rays, keep="last", wavelengths=[WAVELENGTH], reducer=reducer,
-                         out=out)
-        if reducer is not None and world > 1:
-            reducer.allreduce()
+    def step(i, k0=None, k1=None):
+        red = reducers[i % len(reducers)] if reducers else None
+        slot = i % len(reducers) if reducers else 0
+        if red is not None:
+            if comm is not None:
+                torch.cuda.current_stream().wait_event(ev_reduced[slot])     # its last exchange has to be over
+            red.reset()
+        if k0 is not None:
+            k0.record()
+        dev.trace_tensor(system.surfaces, materials, rays, keep="last", wavelengths=[WAVELENGTH], reducer=red, out=out)
+        if k1 is not None:
+            k1.record()
+        if comm is not None:
+            ev_traced[slot].record()
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev_traced[slot])
+                red.allreduce(comm=comm)
+                ev_reduced[slot].record(comm_stream)
+
+    def join_exchange():
+        if comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(comm_stream)
 
     # ---- roofline denominators measured live --------------------------------------------------------------
     dfma = ctypes.c_double()
@@ -321,8 +474,9 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for w in range(max(args.warmup, 3)):
+        step(w)
+    join_exchange()
     torch.cuda.synchronize()
     if rank == 0:
         deadline = time.monotonic() + 2.0
@@ -345,14 +499,8 @@ def main():
     k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record()
     for i in range(args.steps):
-        if reducer is not None:
-            reducer.reset()
-        k0[i].record()
-        dev.trace_tensor(system.surfaces, materials, rays, keep="last", wavelengths=[WAVELENGTH], reducer=reducer,
-                         out=out)
-        k1[i].record()
-        if reducer is not None and world > 1:
-            reducer.allreduce()
+        step(i, k0[i], k1[i])
+    join_exchange()
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -362,15 +510,19 @@ def main():
     elapsed_ms = ev0.elapsed_time(ev1)
     kernel_ms = [a.elapsed_time(b) for a, b in zip(k0, k1)]
     t = torch.tensor([elapsed_ms, statistics.mean(kernel_ms)], dtype=torch.float64, device=f"cuda:{local}")
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, kernel_ms_mean = float(t[0]), float(t[1])
+    kernel_ms_per_rank = [float(x[1]) for x in per_rank]
     total_ray_surfaces = float(source.n_rays) * N_SURFACES * args.steps
     value = total_ray_surfaces / (elapsed_ms * 1e-3)
 
     # sanity: the trace did real work (valid rays came out)
     n_valid = int(torch.isfinite(out[0, :, 0]).sum())
-    stats = reducer.stats() if (reducer is not None and reducer.stats_t is not None) else None
+    last = reducers[(args.steps - 1) % len(reducers)] if reducers else None
+    stats = last.stats() if (last is not None and last.stats_t is not None) else None
 
     # ---- the reference's own output mode (full (2S+1, N, 8) history), device resident: the HBM-bound regime ------
     full_history = None
@@ -418,7 +570,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = float(e2e_src.n_rays) * N_SURFACES * e2e_steps / float(te[0])
     assert np.isfinite(host_out[0, n_e2e // 2, 0])
-    link = link_probe(torch, local) if rank == 0 else None
+    link = link_probe_concurrent(torch, dist, link_probe(torch, local), world, local)
 
     # the unmodified reference call: System.ray_trace(numpy rays) -> full (2S+1, N, 8) history in host memory
     dropin = None
@@ -436,6 +588,16 @@ def main():
                   "api": "System.ray_trace(numpy (N,8)) -> numpy (21, N, 8), the reference's own call",
                   "d2h_bytes": int(hist.nbytes), "h2d_bytes": int(probe.nbytes)}
         del hist
+
+    # ---- BASELINE configs 1-5 on one GPU (the headline above is config 5's size on the relay) -----------------------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        del rays, out
+        torch.cuda.empty_cache()
+        try:
+            configs = config_block(torch, dfma.value)
+        except Exception as exc:                               # reported, not fatal: the headline stands on its own
+            configs = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         rays_per_s_gpu = float(n_rays) / (kernel_ms_mean * 1e-3)
@@ -456,6 +618,7 @@ def main():
                                          "x rays of this launch; algorithmic = 128 B/ray",
                          "peak_source": "DFMA register micro-benchmark run in this process (rtb_measure_dfma_rate)",
                          "algorithmic_instr_per_ray": I_ALG_PER_RAY, "kernel_ms": kernel_ms_mean,
+                         "kernel_ms_per_rank": kernel_ms_per_rank,
                          "executed": None if EXEC_FP64_PER_RAY is None else {
                              "fp64_instr_per_ray": EXEC_FP64_PER_RAY,
                              "achieved": EXEC_FP64_PER_RAY * rays_per_s_gpu / 1e9,
@@ -475,8 +638,12 @@ def main():
                     "d2h_bytes_per_step": n_e2e * 64, "rays_per_gpu_per_step": n_e2e, "steps": e2e_steps,
                     "api": "rtb_trace_host via engine.trace_host (pinned host buffers, keep='last')",
                     "link": link, "cpus_bound_rank0": (len(bound) if bound else None),
-                    "link_frac": (e2e_value / world / N_SURFACES * 128 / 1e9) / link["both_gbps"]},
+                    # bytes the job moves per second over the host links, against what all ranks' links deliver at once
+                    "link_frac": (e2e_value / N_SURFACES * 128 / 1e9) / link["aggregate_gbps"],
+                    "link_frac_note": "e2e bytes/s (64 B in + 64 B out per ray, all ranks) / link.aggregate_gbps, the "
+                                      "rate measured with every rank copying both ways at the same time"},
             "roofline_full_history": full_history,
+            "configs": configs,
             "dropin_full_history": dropin,
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -492,6 +659,8 @@ def main():
                                     "numpy_1core": numpy_leg(1, 2, 20.0),
                                     "numpy_allcores": numpy_leg(cores, 3, 20.0)}
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
