@@ -79,17 +79,42 @@ def spot_statistics(system, initial_material, final_material, sources, slab: int
     return results[0] if single else results
 
 
+def reference_phase(system, mats, source, slab: int, device: int = 0, precision: str = "f64") -> float:
+    """
+    The phase of the bundle's central ray at ``slab`` (the ray in the middle of the source's index space: the chief ray of
+    a fan / collimated / grid source with odd counts), or of the first ray of a 65-ray sample that reaches the slab;
+    0.0 if none does.  Costs one small launch and one device->host read.
+    """
+    n = source.n_rays
+    picks = sorted({n // 2, *np.linspace(0, n - 1, min(n, 64)).astype(np.int64).tolist()})
+    phases = [float(dev.trace_source(system.surfaces, mats, source, first=int(i), count=1, keep=[slab],
+                                     precision=precision, device=device)[0, 0, 6]) for i in [n // 2]]
+    if not np.isfinite(phases[0]):
+        phases = [float(dev.trace_source(system.surfaces, mats, source, first=int(i), count=1, keep=[slab],
+                                         precision=precision, device=device)[0, 0, 6]) for i in picks]
+    good = [p for p in phases if np.isfinite(p)]
+    return good[0] if good else 0.0
+
+
 def pupil_grid(system, initial_material, final_material, source, slab: int, origin, e1, e2, grid_n: int,
-               half_width: float, phase_ref: float = 0.0, precision: str = "f64", device: int = 0,
+               half_width: float, phase_ref: float | None = None, precision: str = "f64", device: int = 0,
                chunk: int = 1 << 27):
     """
     Accumulate sum cos / sum sin / count of the phase of ``source``'s rays at slab ``slab`` on a ``grid_n`` x ``grid_n``
     grid spanning ``[-half_width, half_width)`` in the plane basis ``(origin, e1, e2)``.  Returns the
     :class:`~ray_trace_pb_b200.device.Reducer` (``.grid``, ``.stats()``, ``.psf()``, ``.allreduce()``).
+
+    ``phase_ref`` is subtracted from every ray's phase before cos / sin are taken (a global phase: the PSF does not
+    change).  The default, None, takes the central ray's phase (:func:`reference_phase`): accumulated phases are
+    2 pi / wavelength x optical path -- 1e7 rad for millimetre paths at 532 nm -- and only their small differences
+    matter; referencing them keeps the kernel's sine / cosine arguments small (no large-argument range reduction) and
+    makes the statistics' phase sums (RMS wavefront error) well conditioned.  Pass 0.0 for absolute phases.
     """
     n_slabs = 2 * len(system.surfaces) + 1
     slab = slab + n_slabs if slab < 0 else slab
     mats = _materials(system, initial_material, final_material)
+    if phase_ref is None:
+        phase_ref = reference_phase(system, mats, source, slab, device=device, precision=precision)
     red = dev.Reducer(slab, origin=origin, e1=e1, e2=e2, grid_n=grid_n, half_width=half_width, phase_ref=phase_ref,
                       device=device)
     run = _Launcher(system, mats, device, n_streams=2)

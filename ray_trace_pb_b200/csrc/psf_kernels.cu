@@ -53,8 +53,9 @@ __global__ void dft_matrix_kernel(int M, int G, double df, double cell, double h
 // 64 x 64 tile per block, 16 x 16 threads, 4 x 4 complex accumulators each; thread (ty, tx) owns rows ty + 16 a and
 // columns tx + 16 b, so shared-memory reads are conflict-free (x: broadcast, y: consecutive doubles) and the stores
 // of a warp are contiguous.  gridDim.z splits K: the output tiles of a 257 x 2048 or 257 x 257 product are far too
-// few to fill 148 SMs (160 and 25), so each tile's K loop is shared by several blocks that add their partial sums
-// with red.global.add.f64 into a zeroed C.
+// few to fill 148 SMs (160 and 25), so each tile's K loop is shared by several blocks; block z writes its partial sums
+// to slice z of `part` and sum_partials_kernel adds the slices in order -- the PSF is the same bits run to run (the
+// first version added them with atomics, in whatever order the blocks finished).
 constexpr int kTile = 64, kStep = 16;
 __global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, int k_chunk,
                                                        const double *__restrict__ x_re, const double *__restrict__ x_im,
@@ -100,7 +101,8 @@ __global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, in
         }
         __syncthreads();
     }
-    const bool split = gridDim.z > 1;
+    // (split: c_re / c_im point at the partial-sum slices, slice stride = 2 * Mx * Ny doubles: re plane, im plane)
+    const long long slice = (long long)blockIdx.z * 2 * Mx * Ny;
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -108,15 +110,26 @@ __global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, in
             const int m = m0 + ty + 16 * a, n = n0 + tx + 16 * b;
             if (m < Mx && n < Ny) {
                 const long long o = (long long)m * Ny + n;
-                if (split) {
-                    atomicAdd(c_re + o, ar[a][b]);
-                    atomicAdd(c_im + o, ai[a][b]);
-                } else {
-                    c_re[o] = ar[a][b];
-                    c_im[o] = ai[a][b];
-                }
+                c_re[slice + o] = ar[a][b];
+                c_im[slice + o] = ai[a][b];
             }
         }
+}
+
+// C = sum over the K-split slices, in slice order
+__global__ void sum_partials_kernel(const double *__restrict__ part, int split, long long n, double *__restrict__ c_re,
+                                    double *__restrict__ c_im)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double re = 0.0, im = 0.0;
+        for (int z = 0; z < split; z++) {
+            re += part[(long long)z * 2 * n + i];
+            im += part[(long long)z * 2 * n + n + i];
+        }
+        c_re[i] = re;
+        c_im[i] = im;
+    }
 }
 
 __global__ void abs2_kernel(const double *__restrict__ re, const double *__restrict__ im, long long n,
@@ -128,32 +141,51 @@ __global__ void abs2_kernel(const double *__restrict__ re, const double *__restr
 }
 
 // K split so that the grid is at least ~4 waves of blocks (each block still loops over >= 4 k-steps)
-cudaError_t launch_zgemm(int Mx, int Ny, int K, const double *x_re, const double *x_im, const double *y_re,
-                         const double *y_im, double *c_re, double *c_im, int sm_count, cudaStream_t stream, int *launches)
+int zgemm_split(int Mx, int Ny, int K, int sm_count, int *k_chunk_out)
 {
     const int tiles = ((Mx + kTile - 1) / kTile) * ((Ny + kTile - 1) / kTile);
     int split = (4 * sm_count + tiles - 1) / tiles;
     split = max(1, min(split, K / (4 * kStep)));
-    int k_chunk = ((K + split - 1) / split + kStep - 1) / kStep * kStep;
-    split = (K + k_chunk - 1) / k_chunk;
-    if (split > 1) {
-        cudaError_t e = cudaMemsetAsync(c_re, 0, sizeof(double) * (size_t)Mx * Ny, stream);
-        if (e == cudaSuccess) e = cudaMemsetAsync(c_im, 0, sizeof(double) * (size_t)Mx * Ny, stream);
-        if (e != cudaSuccess) return e;
-    }
+    const int k_chunk = ((K + split - 1) / split + kStep - 1) / kStep * kStep;
+    if (k_chunk_out) *k_chunk_out = k_chunk;
+    return (K + k_chunk - 1) / k_chunk;
+}
+
+// `part`: scratch for split * 2 * Mx * Ny doubles (unused when the product is not split)
+cudaError_t launch_zgemm(int Mx, int Ny, int K, const double *x_re, const double *x_im, const double *y_re,
+                         const double *y_im, double *c_re, double *c_im, double *part, int sm_count, cudaStream_t stream,
+                         int *launches)
+{
+    int k_chunk = K;
+    const int split = zgemm_split(Mx, Ny, K, sm_count, &k_chunk);
     dim3 grid((Ny + kTile - 1) / kTile, (Mx + kTile - 1) / kTile, split);
-    zgemm_nt_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, c_re, c_im);
-    if (launches) (*launches)++;
+    const long long n = (long long)Mx * Ny;
+    if (split == 1) {
+        zgemm_nt_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, c_re, c_im);
+        if (launches) (*launches)++;
+        return cudaGetLastError();
+    }
+    zgemm_nt_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, part, part + n);
+    sum_partials_kernel<<<(unsigned)min((long long)sm_count * 8, (n + 255) / 256), 256, 0, stream>>>(part, split, n, c_re, c_im);
+    if (launches) (*launches) += 2;
     return cudaGetLastError();
 }
 
 } // namespace
 
 // scratch layout (doubles): [0, 2MG) DFT matrix D (re, im) ; [2MG, 4MG) Wt (re, im) ; [4MG, 4MG + 2MM) the field E when
-// the caller does not take it ; then 2GG for the normalised pupil
+// the caller does not take it ; then 2GG for the normalised pupil ; then the K-split partial sums of the larger product
+long long psf_partials_doubles(int G, int M, int sm_count)
+{
+    const long long a = (long long)zgemm_split(M, G, G, sm_count, nullptr) * 2 * M * G;
+    const long long b = (long long)zgemm_split(M, M, G, sm_count, nullptr) * 2 * M * M;
+    return a > b ? a : b;
+}
+
 long long psf_scratch_doubles(int G, int M, int normalize)
 {
-    return 4LL * M * G + 2LL * M * M + (normalize ? 2LL * G * G : 0LL);
+    // (sized for the split a 1-SM .. 256-SM device would choose: the split count only falls as the SM count does)
+    return 4LL * M * G + 2LL * M * M + (normalize ? 2LL * G * G : 0LL) + psf_partials_doubles(G, M, 256);
 }
 
 cudaError_t launch_psf(const double *grid, int G, double half_width, int M, double df, int normalize, double *scratch,
@@ -163,6 +195,7 @@ cudaError_t launch_psf(const double *grid, int G, double half_width, int M, doub
     double *d_re = scratch, *d_im = scratch + mg, *w_re = scratch + 2 * mg, *w_im = scratch + 3 * mg;
     double *e_re = scratch + 4 * mg, *e_im = e_re + mm;
     const double *p_re = grid, *p_im = grid + cells;
+    double *part = scratch + 4 * mg + 2 * mm + (normalize ? 2 * cells : 0);
     int n = 0;
     if (normalize) {
         double *q_re = scratch + 4 * mg + 2 * mm, *q_im = q_re + cells;
@@ -175,14 +208,14 @@ cudaError_t launch_psf(const double *grid, int G, double half_width, int M, doub
     dft_matrix_kernel<<<sm_count * 8, 256, 0, stream>>>(M, G, df, cell, half_width, d_re, d_im);
     n++;
     // Wt[k, v] = sum_u D[k, u] P[v, u]
-    cudaError_t e = launch_zgemm(M, G, G, d_re, d_im, p_re, p_im, w_re, w_im, sm_count, stream, &n);
+    cudaError_t e = launch_zgemm(M, G, G, d_re, d_im, p_re, p_im, w_re, w_im, part, sm_count, stream, &n);
     if (e != cudaSuccess) return e;
     // E[l, k] = sum_v D[l, v] Wt[k, v]   (square pupil grid: the same DFT matrix serves both axes)
     if (field_re && field_im) {
         e_re = field_re;
         e_im = field_im;
     }
-    e = launch_zgemm(M, M, G, d_re, d_im, w_re, w_im, e_re, e_im, sm_count, stream, &n);
+    e = launch_zgemm(M, M, G, d_re, d_im, w_re, w_im, e_re, e_im, part, sm_count, stream, &n);
     if (e != cudaSuccess) return e;
     if (psf_out) {
         abs2_kernel<<<min((long long)sm_count * 8, (mm + 255) / 256), 256, 0, stream>>>(e_re, e_im, mm, psf_out);

@@ -362,6 +362,9 @@ class Reducer:
     ``torch.distributed`` group (NCCL over NVLink): the only communication of a multi-GPU trace.
     ``buckets`` > 1 makes one set per source of a sweep (:func:`trace_sources`): ``stats_t`` is (buckets, 12) and
     ``grid_t`` (buckets, 3, G, G).
+    ``phase_ref`` is a global phase subtracted before cos / sin and the phase sums are formed.  Give it the chief ray's
+    phase (``analysis.reference_phase``; ``analysis.pupil_grid`` does so by default): accumulated phases reach 1e7 rad
+    and with ``phase_ref = 0`` every ray pays for a large-argument range reduction in the kernel.
     """
 
     def __init__(self, slab: int, origin=(0, 0, 0), e1=(1, 0, 0), e2=(0, 1, 0), grid_n: int = 0,
