@@ -253,7 +253,10 @@ def result_array(shape) -> np.ndarray:
     """Where a host-path trace puts its result: recycled pinned memory for big histories, plain NumPy for small."""
     nbytes = int(np.prod(shape)) * 8
     if nbytes >= (8 << 20):
-        return pinned_empty(shape, pooled=True)
+        try:
+            return pinned_empty(shape, pooled=True)
+        except MemoryError:
+            pass        # no page-locked memory left: a pageable result works too (rtb_trace_host stages it), only slower
     return np.empty(shape, dtype=np.float64)
 
 

@@ -299,15 +299,50 @@ def trace_source(surfaces, materials, source: RaySource, first: int = 0, count: 
     engine.set_first_surface_hint(packed, source.degenerate_at_first(surfaces))
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
     opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
-    if n_out == 0:
-        out = None
-    elif out is None:
-        out = torch.empty((n_out, count, 8), dtype=torch.float64, device=f"cuda:{device}")
+    out = _check_out(out, (n_out, count, 8), device)
     src = source.struct
     rc = _ffi.lib().rtb_trace_source(C.byref(packed.sys), C.byref(src), first, count,
                                      out.data_ptr() if out is not None else None, C.byref(opts), device,
                                      _stream_ptr(device))
     _ffi.check(rc)
+    return out
+
+
+def _check_out(out, shape, device):
+    """the caller's output tensor, validated (a wrong shape would be an out-of-bounds device write), or a fresh one"""
+    torch = _torch()
+    if shape[0] == 0:
+        return None
+    if out is None:
+        return torch.empty(shape, dtype=torch.float64, device=f"cuda:{device}")
+    if (tuple(out.shape) != tuple(shape) or out.dtype != torch.float64 or not out.is_contiguous() or not out.is_cuda
+            or out.device.index != device):
+        raise ValueError(f"out must be a contiguous float64 CUDA tensor of shape {tuple(shape)} on device {device}")
+    return out
+
+
+def _trace_sources_grouped(surfaces, materials, sources, wls, first, count, keep, precision, reducer, device, out):
+    """A sweep over more than RTB_MAX_WAVELENGTHS wavelengths through media that need a host table: the sources are
+    launched in groups of <= 8 wavelengths, each into its own rows of the output and its own reduction buckets."""
+    torch = _torch()
+    mode, idx, n_out = engine.resolve_keep(keep, 2 * len(surfaces) + 1)
+    out = _check_out(out, (n_out, len(sources) * count, 8), device)
+    width = _ffi.RTB_MAX_WAVELENGTHS
+    for g in range(0, len(wls), width):
+        group = set(wls[g:g + width])
+        members = [k for k, s in enumerate(sources) if float(s.wavelength) in group
+                   or (g == 0 and not np.isfinite(s.wavelength))]
+        if not members:
+            continue
+        sub = Reducer.view_of(reducer, members) if reducer is not None else None
+        part = trace_sources(surfaces, materials, [sources[k] for k in members], first=first, count=count, keep=keep,
+                             precision=precision, reducer=sub, device=device,
+                             packed=_system_for(surfaces, materials, sorted(group)))
+        if sub is not None:
+            sub.scatter_back()
+        if out is not None:
+            for j, k in enumerate(members):
+                out[:, k * count:(k + 1) * count] = part[:, j * count:(j + 1) * count]
     return out
 
 
@@ -333,14 +368,17 @@ def trace_sources(surfaces, materials, sources, first: int = 0, count: int | Non
         raise ValueError(f"reducer has {reducer.buckets} bucket(s), the sweep has {len(sources)} sources")
     if packed is None:
         wls = sorted({float(s.wavelength) for s in sources if np.isfinite(s.wavelength)})
+        if len(wls) > _ffi.RTB_MAX_WAVELENGTHS:
+            if any(engine.pack_material(m).kind == engine.KIND_TABLE_ONLY for m in materials):
+                # media that only exist as Python code need every wavelength tabulated: one launch per group of 8
+                return _trace_sources_grouped(surfaces, materials, sources, wls, first, count, keep, precision, reducer,
+                                              device, out)
+            wls = None      # every medium has a closed formula: the kernel evaluates it per ray
         packed = _system_for(surfaces, materials, wls or None)
     engine.set_first_surface_hint(packed, all(s.degenerate_at_first(surfaces) for s in sources))
     mode, idx, n_out = engine.resolve_keep(keep, packed.n_slabs)
     opts = engine.make_opts(mode, idx, precision, reducer.struct if reducer is not None else None)
-    if n_out == 0:
-        out = None
-    elif out is None:
-        out = torch.empty((n_out, len(sources) * count, 8), dtype=torch.float64, device=f"cuda:{device}")
+    out = _check_out(out, (n_out, len(sources) * count, 8), device)
     arr = (_ffi.RtbSource * len(sources))(*[s.struct for s in sources])
     rc = _ffi.lib().rtb_trace_sources(C.byref(packed.sys), arr, len(sources), first, count,
                                       out.data_ptr() if out is not None else None, C.byref(opts), device,
@@ -395,6 +433,32 @@ class Reducer:
         s.grid_dev = self.grid_t.data_ptr() if grid_n > 0 else None
         self.struct = s
         self.reset()
+
+    @classmethod
+    def view_of(cls, parent, members):
+        """A reducer over buckets ``members`` of ``parent`` (its own contiguous storage, initialised with the parent's
+        current contents); :meth:`scatter_back` writes the buckets back.  Lets a sweep be launched in groups."""
+        st = parent.struct
+        sub = cls(st.slab, origin=tuple(st.origin), e1=tuple(st.e1), e2=tuple(st.e2), grid_n=parent.grid_n,
+                  half_width=st.grid_half_width, phase_ref=st.phase_ref, stats=parent.stats_t is not None,
+                  device=parent.device, buckets=len(members))
+        idx = _torch().as_tensor(list(members), device=f"cuda:{parent.device}")
+        lead = (lambda t: t if parent.buckets > 1 else t.unsqueeze(0))
+        if sub.stats_t is not None:
+            sub.stats_t.reshape(len(members), -1).copy_(lead(parent.stats_t).index_select(0, idx))
+        if sub.grid_t is not None:
+            sub.grid_t.reshape((len(members),) + tuple(lead(parent.grid_t).shape[1:])).copy_(
+                lead(parent.grid_t).index_select(0, idx))
+        sub._parent, sub._members = parent, idx
+        return sub
+
+    def scatter_back(self):
+        parent, idx = self._parent, self._members
+        lead = (lambda t: t if parent.buckets > 1 else t.unsqueeze(0))
+        if self.stats_t is not None:
+            lead(parent.stats_t).index_copy_(0, idx, self.stats_t.reshape(len(idx), -1))
+        if self.grid_t is not None:
+            lead(parent.grid_t).index_copy_(0, idx, self.grid_t.reshape((len(idx),) + tuple(lead(parent.grid_t).shape[1:])))
 
     def resolve_slab(self, n_slabs: int):
         """allow negative slab indices once the system is known"""

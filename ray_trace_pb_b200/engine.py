@@ -162,7 +162,11 @@ def index_table(materials, wavelengths: np.ndarray) -> np.ndarray:
                 col = np.asarray(m.n(query), dtype=np.float64).reshape(-1)
             except Exception:
                 col = np.full(query.size, np.nan)
-                col[:-1] = np.asarray(m.n(query[:-1]), dtype=np.float64).reshape(-1)
+                head = np.asarray(m.n(query[:-1]), dtype=np.float64).reshape(-1)
+                col[:-1] = np.broadcast_to(head, (query.size - 1,)) if head.size == 1 else head
+            if col.size == 1:
+                # a user material that answers an array with one number: the reference's arithmetic broadcasts it
+                col = np.broadcast_to(col, (query.size,))
             if col.size != query.size:
                 raise ValueError(f"{type(m).__name__}.n() returned {col.size} values for {query.size} wavelengths")
             table[:, j] = col
@@ -419,7 +423,11 @@ def _trace_host_grouped(surfaces, materials, rays, keep, precision, device, redu
     """
     wl = rays[:, 7]
     valid = ~np.isnan(wl)
-    all_wl = np.unique(wl[valid])
+    # grouped by BIT PATTERN, like the device table and the scan that sent the batch here (+0.0 and -0.0 are two
+    # wavelengths to them; grouping by value would hand the same nine patterns back to trace_host for ever)
+    wl_bits = np.ascontiguousarray(wl).view(np.int64)
+    all_bits = np.unique(wl_bits[valid])
+    all_wl = all_bits.view(np.float64)
     width = _ffi.RTB_MAX_WAVELENGTHS
     if all_wl.size > width * MAX_WAVELENGTH_GROUPS:
         bad = sorted({type(m).__name__ for m in materials if pack_material(m).kind == KIND_TABLE_ONLY})
@@ -433,8 +441,7 @@ def _trace_host_grouped(surfaces, materials, rays, keep, precision, device, redu
     elif out.shape != (n_out, n, 8):
         raise ValueError(f"out must have shape {(n_out, n, 8)}")
     for g in range(0, max(all_wl.size, 1), width):
-        group = all_wl[g:g + width]
-        sel = np.isin(wl, group)
+        sel = valid & np.isin(wl_bits, all_bits[g:g + width])
         if g == 0:
             sel |= ~valid                        # NaN-wavelength rays ride with the first group (table's NaN row)
         if not sel.any():
