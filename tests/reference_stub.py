@@ -56,12 +56,13 @@ def pack_surface(s):
     return r
 
 
-def ray_trace(self, rays, initial_material, final_material):        # drop-in for raytrace.py:641-661
+def pack(self, rays, initial_material, final_material):
+    """the host side of the call: the reference's objects -> the C structs (everything but the device call)"""
     materials = [initial_material] + self.materials + [final_material]
     if len(materials) != len(self.surfaces) + 1:
         raise ValueError("length of materials should be len(surfaces) + 1")
     rays = np.ascontiguousarray(np.atleast_2d(rays), dtype=float)                 # (N, 8)
-    S, N = len(self.surfaces), rays.shape[0]
+    S = len(self.surfaces)
     wl = np.unique(rays[~np.isnan(rays[:, 7]), 7])                                # <= RTB_MAX_WAVELENGTHS (8) values
     with np.errstate(all="ignore"):
         table = np.array([np.asarray(m.n(np.append(wl, np.nan)), dtype=float).reshape(-1) for m in materials]).T.copy()
@@ -69,6 +70,12 @@ def ray_trace(self, rays, initial_material, final_material):        # drop-in fo
     mats = (RtbMaterial * (S + 1))(*[RtbMaterial(kind=2) for _ in materials])     # 2 = "host table only": always valid
     sysd = RtbSystem(S, len(wl), surf, mats, wl.ctypes.data_as(C.POINTER(C.c_double)),
                      table.ctypes.data_as(C.POINTER(C.c_double)))
+    return sysd, rays, (surf, mats, wl, table)                                    # (the tuple keeps the memory alive)
+
+
+def ray_trace(self, rays, initial_material, final_material):        # drop-in for raytrace.py:641-661
+    sysd, rays, _keep = pack(self, rays, initial_material, final_material)
+    S, N = len(self.surfaces), rays.shape[0]
     out = np.empty((2 * S + 1, N, 8))
     opts = RtbTraceOpts(precision=0, keep_mode=0)                                 # fp64 exact, full history
     if L.rtb_trace_host(C.byref(sysd), rays.ctypes.data, N, out.ctypes.data, C.byref(opts), 0) != 0:
