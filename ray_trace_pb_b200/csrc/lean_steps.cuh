@@ -82,6 +82,21 @@ __device__ __forceinline__ void unit3_zero_z(bool &ok, double &x, double &y, dou
     z = __hiloint2double(__double2hiint(q) | (__double2hiint(z) & (int)0x80000000), __double2loint(q));
 }
 
+// (x, y, z) / l for a general positive l (Optimistic::rcp + div: every quotient range-tested), the z component allowed to
+// be an exact zero: a perfect lens on the z axis removes the axial part of a vector exactly (dz - (d . n) nz = +0) and
+// measures heights in a plane z = const
+__device__ __forceinline__ void div3_zero_z(bool &ok, double &x, double &y, double &z, double l)
+{
+    const double r = xm::refine_rcp(l);
+    const bool z_is_zero = ((__double2hiint(z) & 0x7fffffff) | __double2loint(z)) == 0;
+    const double qx = xm::div_core(x, l, r), qy = xm::div_core(y, l, r), qz = xm::div_core(z, l, r);
+    ok &= xm::quo_ok(r) & xm::num_ok(x) & xm::num_ok(y) & xm::quo_ok(qx) & xm::quo_ok(qy) &
+          (z_is_zero | (xm::num_ok(z) & xm::quo_ok(qz)));
+    x = qx;
+    y = qy;
+    z = __hiloint2double(__double2hiint(qz) | (__double2hiint(z) & (int)0x80000000), __double2loint(qz));
+}
+
 __device__ __forceinline__ void unit2(bool &ok, double &x, double &y, double l)
 {
     const double r = xm::refine_rcp(l);
@@ -183,6 +198,112 @@ __device__ __forceinline__ bool flat_axial(bool &ok, const DevSurface &s, State 
     r.dz = w * s.nz;
     r.ox = px; r.oy = py; r.oz = pz;
     return on;
+}
+
+// FlatSurface through RefractingSurface.propagate, any normal and input axis (as stored): refracting_step's flat branch
+// with the plain three-term forms, no zero forms.  n . d is the plane propagation's own denominator (the same three
+// products, multiplication commutes), so it is not computed twice.
+__device__ __forceinline__ bool flat_any(bool &ok, const DevSurface &s, State &r, double n1, double ratio, double wl,
+                                         double wl_rcp, bool &kill)
+{
+    const double num = dot3(r.ox - s.cx, r.oy - s.cy, r.oz - s.cz, s.nx, s.ny, s.nz);
+    const double den = dot3(r.dx, r.dy, r.dz, s.nx, s.ny, s.nz);
+    const double den_rcp = xm::refine_rcp(den);
+    const double t = xm::div_core(-num, den, den_rcp);
+    ok &= xm::den_ok(den) & xm::quo_ok(den_rcp) & xm::num_ok(num) & xm::quo_ok(t);
+    const double vx = r.dx * t, vy = r.dy * t, vz = r.dz * t;
+    const double px = r.ox + vx, py = r.oy + vy, pz = r.oz + vz;
+    const double len = with_sign_of(sqrt_chk(ok, sumsq3(vx, vy, vz)), t);      // * prop_direction; t != 0 here
+    r.ph = r.ph + xm::div_core(len * kTwoPi, wl, wl_rcp) * n1;
+    const double rx = px - s.cx, ry = py - s.cy, rz = pz - s.cz;
+    kill = (t < 0.0) | (dot3(r.dx, r.dy, r.dz, s.ax, s.ay, s.az) < 0.0);
+    const bool on = !kill & (fabs(dot3(rx, ry, rz, s.nx, s.ny, s.nz)) < kOnSurfaceTol) & (sumsq3(rx, ry, rz) <= s.ap_sq_max);
+    double bx = r.dy * s.nz - r.dz * s.ny;
+    double by = r.dz * s.nx - r.dx * s.nz;
+    double bz = r.dx * s.ny - r.dy * s.nx;
+    unit3(ok, bx, by, bz, sqrt_unit_chk(ok, sumsq3(bx, by, bz)));
+    double cx = s.ny * bz - s.nz * by;
+    double cy = s.nz * bx - s.nx * bz;
+    double cz = s.nx * by - s.ny * bx;
+    unit3(ok, cx, cy, cz, sqrt_unit_chk(ok, sumsq3(cx, cy, cz)));
+    const double mag_nc = ratio * dot3_np(cx, cy, cz, r.dx, r.dy, r.dz);
+    const double w = with_sign_of(sqrt_chk(ok, 1.0 - mag_nc * mag_nc), den);   // sign(n . d); den != 0 here
+    r.dx = mag_nc * cx + w * s.nx;
+    r.dy = mag_nc * cy + w * s.ny;
+    r.dz = mag_nc * cz + w * s.nz;
+    r.ox = px; r.oy = py; r.oz = pz;
+    return on;
+}
+
+// PerfectLens.propagate (raytrace.py:1601-1801), any normal: perfect_lens_step of surface_steps.cuh without its general
+// zero forms and its "before" slab.  One zero IS handled in line, because whole bundles produce it: a ray that starts
+// exactly in the lens's front focal plane (t = +-0) -- in a 4f train the previous surface sits there.  A beam along the
+// axis (no transverse direction) or through the front focal point (no height) fails the flag; so does a ray that is
+// not culled by the numerical aperture and still has no real cos(theta_2).  `f_rcp`: refined 1 / focal_len (usable,
+// checked per block).  Returns "alive" (not culled by the NA test); the lens has no "at" slab here (kill = false).
+__device__ __forceinline__ bool lens_any(bool &ok, const DevSurface &s, double f_rcp, State &r, double n1, double n2, double wl,
+                                         double wl_rcp)
+{
+    // front / back focal points (raytrace.py:1682-1687)
+    const double fx = s.cx - s.nfx * n1, fy = s.cy - s.nfy * n1, fz = s.cz - s.nfz * n1;
+    const double gx = s.cx + s.nfx * n2, gy = s.cy + s.nfy * n2, gz = s.cz + s.nfz * n2;
+    // the ray in the front focal plane (raytrace.py:1693-1697): to_plane<ZF = true>
+    const double num = dot3(r.ox - fx, r.oy - fy, r.oz - fz, s.nx, s.ny, s.nz);
+    const double den = dot3(r.dx, r.dy, r.dz, s.nx, s.ny, s.nz);
+    const double den_rcp = xm::refine_rcp(den);
+    const bool t_zero = ((__double2hiint(num) & 0x7fffffff) | __double2loint(num)) == 0;
+    const double t_fast = xm::div_core(-num, den, den_rcp);
+    const double t = t_zero ? __dmul_rn(-num, den_rcp) : t_fast;                   // (+-0) / den = the signed zero
+    ok &= xm::den_ok(den) & xm::quo_ok(den_rcp) & (t_zero | (xm::num_ok(num) & xm::quo_ok(t_fast)));
+    const double vx = r.dx * t, vy = r.dy * t, vz = r.dz * t;
+    const double ax = r.ox + vx, ay = r.oy + vy, az = r.oz + vz;
+    const double vv = sumsq3(vx, vy, vz);
+    const int vv_probe = __double2hiint(vv) + (int)0xfcb00000;
+    ok &= t_zero | ((unsigned)vv_probe < 0x7ca00000u);
+    const double len0 = t_zero ? 0.0 : xm::sqrt_core(vv, vv_probe);
+    const double len = (t < 0.0) ? -len0 : len0;                                    // * prop_direction (+1 for t = -0)
+    const double turns = len * kTwoPi;
+    const double ph_ffp = r.ph + (t_zero ? __dmul_rn(turns, wl_rcp) : xm::div_core(turns, wl, wl_rcp)) * n1;
+    // transverse unit vector of the direction (raytrace.py:1704-1715)
+    const double rnd = dot3_np(r.dx, r.dy, r.dz, s.nx, s.ny, s.nz);
+    double px = r.dx - rnd * s.nx, py = r.dy - rnd * s.ny, pz = r.dz - rnd * s.nz;
+    const double pn = sqrt_chk(ok, sumsq3(px, py, pz));
+    ok &= pn > kPerpTol;                                                            // else: left un-normalised (careful path)
+    div3_zero_z(ok, px, py, pz, pn);
+    // height vector in the front focal plane (raytrace.py:1720-1728)
+    const double hx = ax - fx, hy = ay - fy, hz = az - fz;
+    const double hn = sqrt_chk(ok, sumsq3(hx, hy, hz));
+    double ux = hx, uy = hy, uz = hz;
+    div3_zero_z(ok, ux, uy, uz, hn);
+    const double sin_t1 = dot3_np(px, py, pz, r.dx, r.dy, r.dz);                   // raytrace.py:1731
+    // the ray in the back focal plane (raytrace.py:1736-1752)
+    const double scale = (n1 * s.focal_len) * sin_t1;
+    const double bx = scale * px + gx, by = scale * py + gy, bz = scale * pz + gz;
+    const double n2_rcp = xm::refine_rcp(n2);
+    const double s2a = xm::div_core(-hn, s.focal_len, f_rcp);
+    const double sin_t2 = xm::div_core(s2a, n2, n2_rcp);
+    ok &= xm::quo_ok(s2a) & xm::den_ok(n2) & xm::quo_ok(n2_rcp) & xm::num_ok(s2a) & xm::quo_ok(sin_t2);   // (hn is normal)
+    // NA cull (raytrace.py:1757-1760): a culled ray's row is blank whatever else is computed from here on
+    const bool culled = (fabs(sin_t1) > s.sin_alpha) | (fabs(sin_t2) > s.sin_alpha);
+    bool ok2 = true;                                                                // tests that only matter for a surviving ray
+    const double cos_t2 = sqrt_chk(ok2, 1.0 - sin_t2 * sin_t2);
+    const double ex = sin_t2 * ux + cos_t2 * s.nx, ey = sin_t2 * uy + cos_t2 * s.ny, ez = sin_t2 * uz + cos_t2 * s.nz;
+    const double k = xm::div_core(kTwoPi, wl, wl_rcp);
+    const double plane_wave = dot3_np(hx, hy, hz, r.dx, r.dy, r.dz);
+    const double ph_b = (ph_ffp - (k * n1) * plane_wave) + k * ((n1 * n1) * s.focal_len + (n2 * n2) * s.focal_len);
+    // back to the lens plane in the second medium (raytrace.py:1783-1787)
+    const double num2 = dot3(bx - s.cx, by - s.cy, bz - s.cz, s.nx, s.ny, s.nz);
+    const double den2 = dot3(ex, ey, ez, s.nx, s.ny, s.nz);
+    const double den2_rcp = xm::refine_rcp(den2);
+    const double t2 = xm::div_core(-num2, den2, den2_rcp);
+    ok2 &= xm::den_ok(den2) & xm::quo_ok(den2_rcp) & xm::num_ok(num2) & xm::quo_ok(t2);
+    const double wx = ex * t2, wy = ey * t2, wz = ez * t2;
+    const double len2 = with_sign_of(sqrt_chk(ok2, sumsq3(wx, wy, wz)), t2);
+    ok &= culled | ok2;
+    r.ox = bx + wx; r.oy = by + wy; r.oz = bz + wz;
+    r.dx = ex; r.dy = ey; r.dz = ez;
+    r.ph = ph_b + xm::div_core(len2 * kTwoPi, wl, wl_rcp) * n2;
+    return !culled;
 }
 
 } // namespace lean

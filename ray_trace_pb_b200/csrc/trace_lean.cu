@@ -42,7 +42,23 @@ constexpr int kProbeRays = 2048;          // sample size of the probe launch, pe
 constexpr unsigned kProbeOneIn = 200;     // a surface runs the general steps when more than 1 in 200 probe rays failed
 
 // which step a surface runs (decided once per block: kind, axes, the reciprocal radius, the probe's counts)
-enum StepCode : int { kLeanSphere = 0, kLeanFlat = 1, kGeneralRefracting = 2, kGeneralMirror = 3, kGeneralLens = 4 };
+enum StepCode : int { kLeanSphere = 0, kLeanFlat = 1, kGeneralRefracting = 2, kGeneralMirror = 3, kGeneralLens = 4,
+                      kMixedRun = 5, kLeanFlatAny = 6, kLeanLens = 7 };
+
+// the step a surface runs: lean where one exists (spheres on a z axis; flats, on the axis or tilted; perfect lenses),
+// the general step of its kind otherwise or when `general` says so (probe result, unusable reciprocal)
+__host__ __device__ inline int step_code(const DevSurface &s, bool general)
+{
+    const int fallback = (s.kind == RTB_SURF_MIRROR) ? kGeneralMirror
+                                                     : (s.kind == RTB_SURF_PERFECT_LENS) ? kGeneralLens : kGeneralRefracting;
+    if (general) return fallback;
+    if (s.kind == RTB_SURF_SPHERE) return s.z_axis != 0 ? kLeanSphere : fallback;
+    if (s.kind == RTB_SURF_FLAT) return (s.z_axis != 0 && s.z_normal != 0) ? kLeanFlat : kLeanFlatAny;
+    if (s.kind == RTB_SURF_PERFECT_LENS) return kLeanLens;
+    return fallback;
+}
+
+__host__ __device__ inline bool has_lean_step(const DevSurface &s) { return step_code(s, false) != step_code(s, true); }
 
 // per-surface facts every ray needs, decided once per block: one 16-byte shared-memory read per surface
 struct __align__(16) SurfaceShared {
@@ -239,16 +255,15 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
         const bool sane = xm::den_ok(den) && fabs(den) < 4503599627370496.0 && xm::quo_ok(rcp);
         s_c.surf[k].rcp = rcp;
         s_c.surf[k].rcp_ok = sane;
-        // a sphere whose reciprocal radius is unusable goes through the general step (which flags it for the careful path)
-        bool general = ((P.lean_general >> k) & 1ull) != 0 || (!sane && s.kind == RTB_SURF_SPHERE);
+        // a sphere / lens whose reciprocal radius / focal length is unusable goes through the general step (which flags
+        // it for the careful path)
+        bool general = ((P.lean_general >> k) & 1ull) != 0 ||
+                       (!sane && (s.kind == RTB_SURF_SPHERE || s.kind == RTB_SURF_PERFECT_LENS));
         if (!PROBE && P.lean_counts) {
             const unsigned *cnt = P.lean_counts + ((size_t)(SWEEP ? blockIdx.y : 0) * kMaxSurfaces + k) * 2;
             general |= (unsigned long long)cnt[1] * kProbeOneIn > (unsigned long long)cnt[0];
         }
-        int code = (s.kind == RTB_SURF_MIRROR) ? kGeneralMirror : (s.kind == RTB_SURF_PERFECT_LENS) ? kGeneralLens
-                                                                                                     : kGeneralRefracting;
-        if (!general) code = (s.kind == RTB_SURF_SPHERE) ? kLeanSphere : kLeanFlat;
-        s_c.surf[k].code = code;
+        s_c.surf[k].code = step_code(s, general);
     }
     __syncthreads();
     for (int run = threadIdx.x; run < P.lean_n_runs; run += blockDim.x) {
@@ -327,7 +342,8 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                 const int begin = run > 0 ? P.lean_run_end[run - 1] : 0;
                 const int end = P.lean_run_end[run];
                 // (a run is "clean" when the probe left every surface of it on the launcher's step)
-                const int code = s_c.run_clean[run] ? P.lean_run_code[run] : kGeneralRefracting;
+                // (an overridden run goes through the loop that dispatches per surface)
+                const int code = s_c.run_clean[run] ? P.lean_run_code[run] : kMixedRun;
                 if (code == kLeanSphere) {
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
@@ -366,6 +382,98 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
+                } else if (code == kLeanFlatAny) {
+                    for (int k = begin; k < end; k++) {
+                        if (!__any_sync(0xffffffffu, alive)) {
+                            at_valid = false;
+                            break;
+                        }
+                        if (USE_TABLE) {
+                            n1 = pair[0];
+                            pair += 2;
+                        }
+                        const double n2 = USE_TABLE ? 0.0 : eval_index(P.mat[k + 1], wl0);
+                        const double ratio = USE_TABLE ? pair[-1] : xm::div(n1, n2);
+                        bool ok = true, kill;
+                        const bool on = lean::flat_any(ok, P.surf[k], r, n1, ratio, wl0, wl_rcp, kill);
+                        failed = failed | (alive & !ok);
+                        at_valid = alive & ok & !kill;
+                        alive = alive & ok & on;
+                        if (!USE_TABLE) n1 = n2;
+                    }
+                } else if (code == kLeanLens) {
+                    for (int k = begin; k < end; k++) {
+                        if (!__any_sync(0xffffffffu, alive)) {
+                            at_valid = false;
+                            break;
+                        }
+                        double n2;
+                        if (USE_TABLE) {
+                            n1 = pair[0];
+                            n2 = pair[2];
+                            pair += 2;
+                        } else {
+                            n2 = eval_index(P.mat[k + 1], wl0);
+                        }
+                        bool ok = true;
+                        const bool on = lean::lens_any(ok, P.surf[k], s_c.surf[k].rcp, r, n1, n2, wl0, wl_rcp);
+                        failed = failed | (alive & !ok);
+                        at_valid = false;
+                        alive = alive & ok & on;
+                        if (!USE_TABLE) n1 = n2;
+                    }
+                } else if (code == kGeneralLens) {
+                    // a run of perfect lenses: its own loop, so that the hot code of a lens train (the OPM: 4f relays of
+                    // perfect lenses and flats) is this step and the flats' -- not every step the kernel knows
+                    for (int k = begin; k < end; k++) {
+                        if (!__any_sync(0xffffffffu, alive)) {
+                            at_valid = false;
+                            break;
+                        }
+                        const DevSurface &s = P.surf[k];
+                        const SurfaceShared ss = s_c.surf[k];
+                        double ratio, n2;
+                        if (USE_TABLE) {
+                            n1 = pair[0];
+                            ratio = pair[1];
+                            n2 = pair[2];
+                            pair += 2;
+                        } else {
+                            n2 = eval_index(P.mat[k + 1], wl0);
+                            ratio = xm::div(n1, n2);
+                        }
+                        bool ok = true, kill;
+                        const bool on = general_step(s, kGeneralLens, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok, kill);
+                        failed = failed | (alive & !ok);
+                        at_valid = alive & ok & !kill;
+                        alive = alive & ok & on;
+                        if (!USE_TABLE) n1 = n2;
+                    }
+                } else if (code == kGeneralRefracting) {
+                    // tilted / decentred flats and spheres, or ones the launcher keeps off the lean steps
+                    for (int k = begin; k < end; k++) {
+                        if (!__any_sync(0xffffffffu, alive)) {
+                            at_valid = false;
+                            break;
+                        }
+                        const DevSurface &s = P.surf[k];
+                        const SurfaceShared ss = s_c.surf[k];
+                        double ratio, n2 = 0.0;
+                        if (USE_TABLE) {
+                            n1 = pair[0];
+                            ratio = pair[1];
+                            pair += 2;
+                        } else {
+                            n2 = eval_index(P.mat[k + 1], wl0);
+                            ratio = xm::div(n1, n2);
+                        }
+                        bool ok = true, kill;
+                        const bool on = general_step(s, kGeneralRefracting, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok, kill);
+                        failed = failed | (alive & !ok);
+                        at_valid = alive & ok & !kill;
+                        alive = alive & ok & on;
+                        if (!USE_TABLE) n1 = n2;
+                    }
                 } else {
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
@@ -386,12 +494,18 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         }
                         bool ok = true, kill;
                         bool on;
-                        if (ss.code == kLeanSphere)
+                        if (ss.code == kLeanSphere) {
                             on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp, kill);
-                        else if (ss.code == kLeanFlat)
+                        } else if (ss.code == kLeanFlat) {
                             on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
-                        else
+                        } else if (ss.code == kLeanFlatAny) {
+                            on = lean::flat_any(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
+                        } else if (ss.code == kLeanLens) {
+                            on = lean::lens_any(ok, s, ss.rcp, r, n1, n2, wl0, wl_rcp);
+                            kill = false;
+                        } else {
                             on = general_step(s, ss.code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok, kill);
+                        }
                         failed = failed | (alive & !ok);
                         at_valid = alive & ok & !kill;
                         alive = alive & ok & on;
@@ -428,6 +542,10 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                     on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp, kill);
                 else if (code == kLeanFlat)
                     on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
+                else if (code == kLeanFlatAny)
+                    on = lean::flat_any(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
+                else if (code == kLeanLens)
+                    on = lean::lens_any(ok, s, ss.rcp, r, n1, n2, wl0, wl_rcp);
                 else
                     on = general_step(s, code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok, kill);
                 atomicAdd(my_counts + 2 * k, 1u);
@@ -503,6 +621,10 @@ cudaError_t launch_lean_pick(const TraceParams &P, unsigned blocks, unsigned *pr
 
 } // namespace
 
+// share of surfaces with a lean step below which a system stays with trace_f64.cu (rtb_tune "lean_min_share_pct")
+int g_lean_min_share_pct = 75;
+void set_lean_min_share_pct(int pct) { g_lean_min_share_pct = pct; }
+
 // What the lean kernel traces: fp64 exact, nothing stored but the final slab (or nothing at all), no reduction or one at
 // an after-surface slab, not the intersect-only operator.
 bool lean_eligible(const TraceParams &P)
@@ -518,9 +640,9 @@ bool lean_eligible(const TraceParams &P)
     int n_lean = 0;
     for (int k = 0; k < P.n_surf; k++) {
         const DevSurface &s = P.surf[k];
-        n_lean += (s.kind == RTB_SURF_SPHERE && s.z_axis != 0) || (s.kind == RTB_SURF_FLAT && s.z_axis != 0 && s.z_normal != 0);
+        n_lean += has_lean_step(s);
     }
-    if (4 * n_lean < 3 * P.n_surf) return false;
+    if (100 * n_lean < g_lean_min_share_pct * P.n_surf) return false;
     if (P.red.slab < 0 && !P.any_store) return false;      // nothing to do: leave it to the general kernel's conventions
     return P.n_surf > 0;
 }
@@ -537,9 +659,7 @@ cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_
     P.lean_general = 0ull;
     for (int k = 0; k < P.n_surf; k++) {
         const DevSurface &s = P.surf[k];
-        const bool lean_kind = (s.kind == RTB_SURF_SPHERE && s.z_axis != 0) ||
-                               (s.kind == RTB_SURF_FLAT && s.z_axis != 0 && s.z_normal != 0);
-        if (!lean_kind) P.lean_general |= 1ull << k;
+        if (!has_lean_step(s)) P.lean_general |= 1ull << k;
     }
     // runs of equal step codes, split where the reduction samples
     {
@@ -549,12 +669,10 @@ cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_
         int prev = -1;
         for (int k = 0; k < P.n_surf; k++) {
             const DevSurface &s = P.surf[k];
-            int code = (s.kind == RTB_SURF_MIRROR) ? kGeneralMirror : (s.kind == RTB_SURF_PERFECT_LENS) ? kGeneralLens
-                                                                                                         : kGeneralRefracting;
-            const bool sane = std::isfinite(s.radius) && fabs(s.radius) > 1e-150 && fabs(s.radius) < 4503599627370496.0;
-            if (!((P.lean_general >> k) & 1ull) && (s.kind != RTB_SURF_SPHERE || sane))
-                code = (s.kind == RTB_SURF_SPHERE) ? kLeanSphere : kLeanFlat;
-            if (code >= kGeneralRefracting) code = kGeneralRefracting;      // one run type for every general step
+            const double den = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
+            const bool needs_rcp = s.kind == RTB_SURF_SPHERE || s.kind == RTB_SURF_PERFECT_LENS;
+            const bool sane = std::isfinite(den) && fabs(den) > 1e-150 && fabs(den) < 4503599627370496.0;
+            const int code = step_code(s, ((P.lean_general >> k) & 1ull) != 0 || (needs_rcp && !sane));
             if (code != prev) P.lean_n_runs++;
             P.lean_run_code[P.lean_n_runs - 1] = (uint8_t)code;
             P.lean_run_end[P.lean_n_runs - 1] = (uint8_t)(k + 1);
