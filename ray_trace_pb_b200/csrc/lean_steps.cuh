@@ -157,45 +157,88 @@ __device__ __forceinline__ bool sphere_axial(bool &ok, const DevSurface &s, doub
     return on;
 }
 
+// (x, y) / l, l = sqrt_unit_chk(x^2 + y^2), each component allowed to be an exact zero (the zero-tolerant flat step)
+__device__ __forceinline__ void unit2_zero(bool &ok, double &x, double &y, double l)
+{
+    const double r = xm::refine_rcp(l);
+    const bool x_zero = ((__double2hiint(x) & 0x7fffffff) | __double2loint(x)) == 0;
+    const bool y_zero = ((__double2hiint(y) & 0x7fffffff) | __double2loint(y)) == 0;
+    ok &= (xm::num_ok(x) | x_zero) & (xm::num_ok(y) | y_zero);
+    const double qx = xm::div_core(x, l, r), qy = xm::div_core(y, l, r);
+    x = __hiloint2double(__double2hiint(qx) | (__double2hiint(x) & (int)0x80000000), __double2loint(qx));
+    y = __hiloint2double(__double2hiint(qy) | (__double2hiint(y) & (int)0x80000000), __double2loint(qy));
+}
+
 // FlatSurface through RefractingSurface.propagate, normal (+-0, +-0, +-1) and input axis (0, 0, +-1).
 // With that normal the reference's arithmetic collapses exactly (x - (+-0) = x, (+-0) - x = -x, x + (+-0) = x for
-// x != 0; every such x is checked non-zero through the flag):
+// x != 0):
 //   t        = -((oz - cz) nz) / (dz nz)                                   (to_plane's axis shortcut)
 //   d x n    = (dy nz, -(dx nz), +-0)            n x nb = (-(nz nb_y), nz nb_x, +-0)
-//   nc . d   = nc_x dx + nc_y dy  (same sign, no cancellation)              n . d = nz dz
-//   d'       = (m nc_x, m nc_y, w nz)
-// The signs of the exact zeros never reach a result.  A ray along the normal (d x n = 0), one that starts on the plane
-// (t = +-0) or lies in the x = 0 / y = 0 plane fails the flag.
+//   nc . d   = (0 + nc_x dx) + nc_y dy                                      n . d = nz dz
+//   d'       = (m nc_x + w nx, m nc_y + w ny, w nz)
+// ZF = false: the hot form.  Every quantity above is checked non-zero through the flag, the +-0 terms are dropped.
+// ZF = true: the form for the surfaces where the probe found whole bundles failing that -- what the reference's scripts
+// put in front of almost every system: rays that START ON the plane (t = +-0, whose sign is that of the full three-term
+// sum), rays ALONG the normal (d x n = 0: the reference's 0/0 -> NaN -> 0 fix-ups leave nb = nc = (+0, +0, +0), and the
+// general formulas evaluated with that nc give d' = +-n with the reference's zero signs), rays in the planes x = 0 or
+// y = 0 (one exact-zero component of d x n).
+template <bool ZF>
 __device__ __forceinline__ bool flat_axial(bool &ok, const DevSurface &s, State &r, double n1, double ratio, double wl,
                                            double wl_rcp, bool &kill)
 {
     // propagate_ray2plane (raytrace.py:241-306) with exclude_backward_propagation (303-304)
-    const double num = (r.oz - s.cz) * s.nz;
+    double num = (r.oz - s.cz) * s.nz;
     const double den = r.dz * s.nz;
+    const bool t_zero = ZF && ((__double2hiint(num) & 0x7fffffff) | __double2loint(num)) == 0;
+    if (ZF && t_zero) num = ((r.ox - s.cx) * s.nx + (r.oy - s.cy) * s.ny) + num;      // the sign of the zero
     const double den_rcp = xm::refine_rcp(den);
-    const double t = xm::div_core(-num, den, den_rcp);
-    ok &= xm::den_ok(den) & xm::quo_ok(den_rcp) & xm::num_ok(num) & xm::quo_ok(t);
+    const double t_fast = xm::div_core(-num, den, den_rcp);
+    const double t = t_zero ? __dmul_rn(-num, den_rcp) : t_fast;
+    ok &= xm::den_ok(den) & xm::quo_ok(den_rcp) & (t_zero | (xm::num_ok(num) & xm::quo_ok(t_fast)));
     const double vx = r.dx * t, vy = r.dy * t, vz = r.dz * t;
     const double px = r.ox + vx, py = r.oy + vy, pz = r.oz + vz;
-    const double len = with_sign_of(sqrt_chk(ok, sumsq3(vx, vy, vz)), t);      // * prop_direction; t != 0 here
-    r.ph = r.ph + xm::div_core(len * kTwoPi, wl, wl_rcp) * n1;
+    const double vv = sumsq3(vx, vy, vz);
+    const int vv_probe = __double2hiint(vv) + (int)0xfcb00000;
+    ok &= t_zero | ((unsigned)vv_probe < 0x7ca00000u);
+    const double root = with_sign_of(xm::sqrt_core(vv, vv_probe), t);                 // * prop_direction
+    const double len = t_zero ? 0.0 : root;                                           // (+1 for t = -0)
+    const double turns = len * kTwoPi;
+    r.ph = r.ph + (t_zero ? __dmul_rn(turns, wl_rcp) : xm::div_core(turns, wl, wl_rcp)) * n1;
     // is_pt_on_surface (raytrace.py:1339-1347), front-side cull (1187-1192)
     const double rx = px - s.cx, ry = py - s.cy, rz = pz - s.cz;
     kill = (t < 0.0) | (r.dz * s.az < 0.0);
     const bool on = !kill & (fabs(rz * s.nz) < kOnSurfaceTol) & (sumsq3(rx, ry, rz) <= s.ap_sq_max);
     // Snell in the plane
     double bx = r.dy * s.nz, by = -(r.dx * s.nz);
-    unit2(ok, bx, by, sqrt_unit_chk(ok, bx * bx + by * by));
-    double cx = -(s.nz * by), cy = s.nz * bx;
-    unit2(ok, cx, cy, sqrt_unit_chk(ok, cx * cx + cy * cy));
-    const double mag_nc = ratio * (cx * r.dx + cy * r.dy);
-    const double w = with_sign_of(sqrt_chk(ok, 1.0 - mag_nc * mag_nc), den);   // sign(n . d) = sign(nz dz), non-zero
-    const double ex = mag_nc * cx, ey = mag_nc * cy;
-    // m nc_x + w (+-0) keeps m nc_x only if it is not itself a zero: products this small leave the lean path
-    ok &= xm::num_ok(ex) & xm::num_ok(ey);
+    double ex, ey;
+    if (!ZF) {
+        unit2(ok, bx, by, sqrt_unit_chk(ok, bx * bx + by * by));
+        double cx = -(s.nz * by), cy = s.nz * bx;
+        unit2(ok, cx, cy, sqrt_unit_chk(ok, cx * cx + cy * cy));
+        const double mag_nc = ratio * (cx * r.dx + cy * r.dy);
+        const double w = with_sign_of(sqrt_chk(ok, 1.0 - mag_nc * mag_nc), den);      // sign(n . d) = sign(nz dz), non-zero
+        ex = mag_nc * cx;
+        ey = mag_nc * cy;
+        // m nc_x + w (+-0) keeps m nc_x only if it is not itself a zero: products this small leave the lean path
+        ok &= xm::num_ok(ex) & xm::num_ok(ey);
+        r.dz = w * s.nz;
+    } else {
+        const bool along = (((__double2hiint(bx) | __double2hiint(by)) & 0x7fffffff) | __double2loint(bx) | __double2loint(by)) == 0;
+        bool basis_ok = true;
+        unit2_zero(basis_ok, bx, by, sqrt_unit_chk(basis_ok, bx * bx + by * by));
+        double cx = -(s.nz * by), cy = s.nz * bx;
+        unit2_zero(basis_ok, cx, cy, sqrt_unit_chk(basis_ok, cx * cx + cy * cy));
+        ok &= along | basis_ok;
+        cx = along ? 0.0 : cx;
+        cy = along ? 0.0 : cy;
+        const double mag_nc = ratio * ((0.0 + cx * r.dx) + cy * r.dy);
+        const double w = with_sign_of(sqrt_chk(ok, 1.0 - mag_nc * mag_nc), den);
+        ex = mag_nc * cx + w * s.nx;
+        ey = mag_nc * cy + w * s.ny;
+        r.dz = w * s.nz;
+    }
     r.dx = ex;
     r.dy = ey;
-    r.dz = w * s.nz;
     r.ox = px; r.oy = py; r.oz = pz;
     return on;
 }

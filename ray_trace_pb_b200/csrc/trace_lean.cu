@@ -43,7 +43,7 @@ constexpr unsigned kProbeOneIn = 200;     // a surface runs the general steps wh
 
 // which step a surface runs (decided once per block: kind, axes, the reciprocal radius, the probe's counts)
 enum StepCode : int { kLeanSphere = 0, kLeanFlat = 1, kGeneralRefracting = 2, kGeneralMirror = 3, kGeneralLens = 4,
-                      kMixedRun = 5, kLeanFlatAny = 6, kLeanLens = 7 };
+                      kMixedRun = 5, kLeanFlatAny = 6, kLeanLens = 7, kLeanFlatZ = 8 };
 
 // the step a surface runs: lean where one exists (spheres on a z axis; flats, on the axis or tilted; perfect lenses),
 // the general step of its kind otherwise or when `general` says so (probe result, unusable reciprocal)
@@ -51,14 +51,17 @@ __host__ __device__ inline int step_code(const DevSurface &s, bool general)
 {
     const int fallback = (s.kind == RTB_SURF_MIRROR) ? kGeneralMirror
                                                      : (s.kind == RTB_SURF_PERFECT_LENS) ? kGeneralLens : kGeneralRefracting;
+    // (an on-axis flat keeps a lean step when the probe overrides it: the zero-tolerant form, which takes every bundle
+    // the general step takes)
+    if (s.kind == RTB_SURF_FLAT && s.z_axis != 0 && s.z_normal != 0) return general ? kLeanFlatZ : kLeanFlat;
     if (general) return fallback;
     if (s.kind == RTB_SURF_SPHERE) return s.z_axis != 0 ? kLeanSphere : fallback;
-    if (s.kind == RTB_SURF_FLAT) return (s.z_axis != 0 && s.z_normal != 0) ? kLeanFlat : kLeanFlatAny;
+    if (s.kind == RTB_SURF_FLAT) return kLeanFlatAny;
     if (s.kind == RTB_SURF_PERFECT_LENS) return kLeanLens;
     return fallback;
 }
 
-__host__ __device__ inline bool has_lean_step(const DevSurface &s) { return step_code(s, false) != step_code(s, true); }
+__host__ __device__ inline bool has_lean_step(const DevSurface &s) { return step_code(s, false) < kGeneralRefracting || step_code(s, false) > kMixedRun; }
 
 // per-surface facts every ray needs, decided once per block: one 16-byte shared-memory read per surface
 struct __align__(16) SurfaceShared {
@@ -223,7 +226,10 @@ __device__ __forceinline__ bool general_step(const DevSurface &s, int code, doub
 // ---- the kernel --------------------------------------------------------------------------------------------------
 // USE_TABLE / FROM_SOURCE as in trace_f64.cu.  SWEEP: blockIdx.y picks the source, its output rows and its reduction
 // bucket (rtb_trace_sources).  PROBE: the probe launch -- a strided sample of the rays, per-surface recovery, counts only.
-template <bool USE_TABLE, bool FROM_SOURCE, bool SWEEP, bool PROBE>
+// KINDS   0: the instantiation for systems of spheres and on-axis flats only (lens trains: the relay, doublets, the
+//            achromat systems) -- it does not carry the perfect-lens, tilted-flat and mirror steps, whose mere presence
+//            costs the sphere loop 2 % through register allocation; 1: every step.
+template <bool USE_TABLE, bool FROM_SOURCE, bool SWEEP, bool PROBE, int KINDS>
 __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kernel(const __grid_constant__ TraceParams P,
                                                                                   unsigned *probe_counts)
 {
@@ -376,13 +382,13 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         const double n2 = USE_TABLE ? 0.0 : eval_index(P.mat[k + 1], wl0);
                         const double ratio = USE_TABLE ? pair[-1] : xm::div(n1, n2);
                         bool ok = true, kill;
-                        const bool on = lean::flat_axial(ok, P.surf[k], r, n1, ratio, wl0, wl_rcp, kill);
+                        const bool on = lean::flat_axial<false>(ok, P.surf[k], r, n1, ratio, wl0, wl_rcp, kill);
                         failed = failed | (alive & !ok);
                         at_valid = alive & ok & !kill;
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
-                } else if (code == kLeanFlatAny) {
+                } else if (KINDS >= 1 && code == kLeanFlatAny) {
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
                             at_valid = false;
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
-                } else if (code == kLeanLens) {
+                } else if (KINDS >= 1 && code == kLeanLens) {
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
                             at_valid = false;
@@ -422,7 +428,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
-                } else if (code == kGeneralLens) {
+                } else if (KINDS >= 1 && code == kGeneralLens) {
                     // a run of perfect lenses: its own loop, so that the hot code of a lens train (the OPM: 4f relays of
                     // perfect lenses and flats) is this step and the flats' -- not every step the kernel knows
                     for (int k = begin; k < end; k++) {
@@ -497,14 +503,18 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         if (ss.code == kLeanSphere) {
                             on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp, kill);
                         } else if (ss.code == kLeanFlat) {
-                            on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
-                        } else if (ss.code == kLeanFlatAny) {
+                            on = lean::flat_axial<false>(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
+                        } else if (ss.code == kLeanFlatZ) {
+                            on = lean::flat_axial<true>(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
+                        } else if (KINDS >= 1 && ss.code == kLeanFlatAny) {
                             on = lean::flat_any(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
-                        } else if (ss.code == kLeanLens) {
+                        } else if (KINDS >= 1 && ss.code == kLeanLens) {
                             on = lean::lens_any(ok, s, ss.rcp, r, n1, n2, wl0, wl_rcp);
                             kill = false;
                         } else {
-                            on = general_step(s, ss.code, ss.rcp, ss.rcp_ok != 0, r, n1, n2, ratio, wl0, wl_rcp, ok, kill);
+                            // (KINDS = 0: the launcher has made sure that only refracting surfaces get here)
+                            on = general_step(s, KINDS >= 1 ? ss.code : (int)kGeneralRefracting, ss.rcp, ss.rcp_ok != 0, r, n1,
+                                              n2, ratio, wl0, wl_rcp, ok, kill);
                         }
                         failed = failed | (alive & !ok);
                         at_valid = alive & ok & !kill;
@@ -541,7 +551,9 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                 if (code == kLeanSphere)
                     on = lean::sphere_axial(ok, s, ss.rcp, r, n1, ratio, wl0, wl_rcp, kill);
                 else if (code == kLeanFlat)
-                    on = lean::flat_axial(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
+                    on = lean::flat_axial<false>(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
+                else if (code == kLeanFlatZ)
+                    on = lean::flat_axial<true>(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
                 else if (code == kLeanFlatAny)
                     on = lean::flat_any(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
                 else if (code == kLeanLens)
@@ -592,12 +604,25 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
     if (reducing) flush_tally(red, s_tally);
 }
 
+// systems of spheres and on-axis flats only
+bool refracting_only(const TraceParams &P)
+{
+    for (int k = 0; k < P.n_surf; k++) {
+        const DevSurface &s = P.surf[k];
+        if (!(s.kind == RTB_SURF_SPHERE || (s.kind == RTB_SURF_FLAT && s.z_axis != 0 && s.z_normal != 0))) return false;
+    }
+    return true;
+}
+
 template <bool T, bool S, bool W, bool PR>
 cudaError_t launch_lean_one(const TraceParams &P, unsigned blocks, unsigned n_y, unsigned *probe_counts, cudaStream_t stream)
 {
     size_t dyn = T ? 2 * sizeof(double) * (size_t)(P.n_wl + 1) * (size_t)(P.n_surf + 1) : 0;
     if (!PR && P.red.slab >= 0 && P.red.stats) dyn += sizeof(double) * 12 * kLeanThreads;
-    trace_lean_kernel<T, S, W, PR><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
+    if (!PR && refracting_only(P))
+        trace_lean_kernel<T, S, W, PR, 0><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
+    else
+        trace_lean_kernel<T, S, W, PR, 1><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
     return cudaGetLastError();
 }
 

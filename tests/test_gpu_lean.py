@@ -226,8 +226,8 @@ def test_probe_finds_the_surfaces_that_need_zero_forms(rt, rtm, dev, torch, lean
     counts = lean.probe_counts(len(system.surfaces))
     assert (counts[:, 0] > 1500).all() and (counts[:, 1] == 0).all(), counts
     # the plano-convex lens of config 1: the beam runs along the normal of both flats' common axis -- the first flat
-    # sees d x n = 0 for every ray, the lens and the flat behind it only for the few rays on the axis (one per azimuth)
-    # and in the planes x = 0 and y = 0
+    # sees d x n = 0 for every ray (the main launch then runs its zero-tolerant lean step there), the lens and the flat
+    # behind it only for the few rays on the axis (one per azimuth) and in the planes x = 0 and y = 0
     system, m_in, m_out, _ = systems.plano_convex(rt, rtm)
     mats = [m_in] + list(system.materials) + [m_out]
     src = dev.RaySource.collimated([0, 0, -5], 20.0, 301, 0.5, nphis=301)
