@@ -455,17 +455,16 @@ def main():
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
-    traffic_per_ray = None
+    # what the dominant kernel executes per ray, from its ncu capture (profiles/r02_traffic.json: opcode counts and DRAM
+    # bytes of trace_lean_kernel on this workload)
+    prof = {}
     try:
-        traffic_per_ray = float(json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())["dram_bytes_per_ray"])
+        tj = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())
+        prof = tj if args.reduce != "none" else tj["fast_kernel"]
     except Exception:
         pass
-    EXEC_FP64_PER_RAY = None
-    try:
-        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
-        EXEC_FP64_PER_RAY = float((tj if args.reduce != "none" else tj["fast_kernel"])["fp64_pipe_instr_per_ray"])
-    except Exception:
-        pass
+    traffic_per_ray = prof.get("dram_bytes_per_ray")
+    EXEC_FP64_PER_RAY = prof.get("fp64_pipe_instr_per_ray")
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
 
@@ -611,25 +610,30 @@ def main():
                        "grid": GRID_N if args.reduce == "grid" else 0,
                        "l2": "inputs (8 GB/GPU at the default size) are larger than L2; no flush needed",
                        "valid_rays_rank0": n_valid, "parity": "fp64 bit-exact mode"},
-            "roofline": {"bound": "fp64", "achieved": achieved_inst / 1e9, "peak": dfma.value / 1e9,
-                         "unit": "G FP64-pipe instr/s", "frac": achieved_inst / dfma.value,
+            # frac = FP64-pipe instructions the kernel EXECUTES per second / the measured DFMA rate: the share of the FP64
+            # pipe's issue slots in use, which is what ncu's sm__pipe_fp64_cycles_active reports for the same kernel
+            # (profiles/r02_bench_step_ncu_summary.txt).  The algorithmic form of SURVEY.md 8d (2900 instr/ray: every
+            # division and square root counted as its own 8-instruction sequence, no shared reciprocals) is kept below.
+            "roofline": {"bound": "fp64",
+                         "achieved": None if EXEC_FP64_PER_RAY is None else EXEC_FP64_PER_RAY * rays_per_s_gpu / 1e9,
+                         "peak": dfma.value / 1e9, "unit": "G FP64-pipe instr/s",
+                         "frac": None if EXEC_FP64_PER_RAY is None else EXEC_FP64_PER_RAY * rays_per_s_gpu / dfma.value,
                          "traffic": None if traffic_per_ray is None else traffic_per_ray * n_rays,
-                         "traffic_note": "DRAM bytes per launch = ncu dram__bytes_read+write per ray (profiles/r01_traffic.json) "
+                         "traffic_note": "DRAM bytes per launch = ncu dram__bytes_read+write per ray (profiles/r02_traffic.json) "
                                          "x rays of this launch; algorithmic = 128 B/ray",
                          "peak_source": "DFMA register micro-benchmark run in this process (rtb_measure_dfma_rate)",
-                         "algorithmic_instr_per_ray": I_ALG_PER_RAY, "kernel_ms": kernel_ms_mean,
+                         "kernel": "trace_lean_kernel (csrc/trace_lean.cu)", "kernel_ms": kernel_ms_mean,
                          "kernel_ms_per_rank": kernel_ms_per_rank,
-                         "executed": None if EXEC_FP64_PER_RAY is None else {
-                             "fp64_instr_per_ray": EXEC_FP64_PER_RAY,
-                             "achieved": EXEC_FP64_PER_RAY * rays_per_s_gpu / 1e9,
-                             "frac_of_peak": EXEC_FP64_PER_RAY * rays_per_s_gpu / dfma.value,
-                             "one_chain_per_warp_peak": dfma_chain.value / 1e9,
-                             "frac_of_one_chain_peak": EXEC_FP64_PER_RAY * rays_per_s_gpu / dfma_chain.value,
-                             "note": "FP64-pipe instructions the kernel executes per ray (ncu opcode counts, "
-                                     "profiles/r01_traffic.json) against the DFMA rate of 8 independent chains per thread "
-                                     "(peak) and of one dependent chain per warp (rtb_measure_dfma_chain_rate): an FP64 "
-                                     "instruction that follows another warp's costs the B200 pipe 3 cycles instead of 2 "
-                                     "(DESIGN.md 4a)"},
+                         "executed": {"fp64_instr_per_ray": EXEC_FP64_PER_RAY,
+                                      "other_instr_per_ray": prof.get("other_instr_per_ray"),
+                                      "ncu_fp64_pipe_active_pct": prof.get("fp64_pipe_active_pct"),
+                                      "note": "per-ray counts from ncu opcode statistics; the kernel is bound by the "
+                                              "sub-partition's operand-read port, which every pipe shares: cycles per "
+                                              "ray ~ 2 x FP64 + 1 per DFMA with three register operands + 1 per other "
+                                              "instruction (DESIGN.md 4a, tools/ubench/rf_bandwidth.cu)"},
+                         "algorithmic": {"instr_per_ray": I_ALG_PER_RAY, "achieved": achieved_inst / 1e9,
+                                         "frac": achieved_inst / dfma.value,
+                                         "dependent_dfma_chain_rate": dfma_chain.value / 1e9},
                          "flops_form": {"achieved_tflops": F_ALG_PER_RAY * rays_per_s_gpu / 1e12,
                                         "peak_tflops_fma2": 2 * dfma.value / 1e12},
                          "hbm": {"achieved": BYTES_PER_RAY * rays_per_s_gpu / 1e9, "peak": hbm_peak, "unit": "GB/s",

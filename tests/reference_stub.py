@@ -64,7 +64,7 @@ def pack(self, rays, initial_material, final_material):
     rays = np.ascontiguousarray(np.atleast_2d(rays), dtype=float)                 # (N, 8)
     S = len(self.surfaces)
     wl = np.unique(rays[~np.isnan(rays[:, 7]), 7])                                # <= RTB_MAX_WAVELENGTHS (8) values
-    with np.errstate(all="ignore"):
+    with np.errstate(all="ignore"):                                               # (len(wl)+1, S+1): the user's own n()
         table = np.array([np.asarray(m.n(np.append(wl, np.nan)), dtype=float).reshape(-1) for m in materials]).T.copy()
     surf = (RtbSurface * S)(*map(pack_surface, self.surfaces))
     mats = (RtbMaterial * (S + 1))(*[RtbMaterial(kind=2) for _ in materials])     # 2 = "host table only": always valid
