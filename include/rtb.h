@@ -233,6 +233,8 @@ int64_t rtb_launch_count(void);
  *                    The environment variable RTB_LEAN_MIN_RAYS sets the initial value.
  *   "lean_min_share_pct"  that kernel pair takes a system only when at least this share (per cent, default 75) of its
  *                    surfaces are on-axis spheres / flats, the ones it has lean steps for (RTB_LEAN_MIN_SHARE_PCT).
+ *   "psf_dmma"       1 (default): the PSF contraction runs on the FP64 tensor path (mma.sync.m8n8k4.f64); 0: the SIMT
+ *                    register-tiled kernel.  Same sums in a different order (agreement ~1e-13 relative).
  *   "keep_probe_counts" test hook: 1 = every lean launch synchronises and keeps its probe's per-surface counts for
  *                    rtb_last_probe_counts().
  *   "host_fail_chunk" test hook: rtb_trace_host returns RTB_ERR_CUDA when it is about to launch chunk n (0-based) of a

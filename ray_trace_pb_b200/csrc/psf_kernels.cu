@@ -116,6 +116,85 @@ __global__ void __launch_bounds__(256) zgemm_nt_kernel(int Mx, int Ny, int K, in
         }
 }
 
+// The same product on the FP64 tensor path: mma.sync.m8n8k4.f64 (DMMA).  64 x 64 tile per block, 8 warps as 4 (m) x 2 (n),
+// each warp 16 x 32 = 2 x 4 fragments of 8 x 8; per k-step of 4 a warp loads 4 A fragments (X re / im of its two row
+// groups) and 8 B fragments from shared memory and issues 32 DMMAs (re += Xr Yr; re += (-Xi) Yi; im += Xr Yi; im += Xi Yr).
+// A DMMA does the work of eight DFMAs with four register operands, which is what the operand-read port
+// leaves room for.  Shared tiles are k-major with a row stride of 68 doubles: a fragment read touches 16 distinct
+// 8-byte banks per half warp.
+constexpr int kPad = 68;
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) zgemm_nt_dmma_kernel(int Mx, int Ny, int K, int k_chunk,
+                                                            const double *__restrict__ x_re, const double *__restrict__ x_im,
+                                                            const double *__restrict__ y_re, const double *__restrict__ y_im,
+                                                            double *__restrict__ c_re, double *__restrict__ c_im)
+{
+    __shared__ double sxr[kStep][kPad], sxi[kStep][kPad], syr[kStep][kPad], syi[kStep][kPad];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 1, wn = warp & 1;               // this warp's 16 x 32 piece of the tile
+    const int g = lane >> 2, t = lane & 3;                 // fragment coordinates: group (row / column), thread in group (k)
+    const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
+    const int k_begin = blockIdx.z * k_chunk, k_end = min(K, k_begin + k_chunk);
+    double cr[2][4][2] = {}, ci[2][4][2] = {};
+    for (int k0 = k_begin; k0 < k_end; k0 += kStep) {
+        for (int e = threadIdx.x; e < kTile * kStep; e += 256) {
+            const int r = e / kStep, kk = e % kStep;
+            const int k = k0 + kk;
+            const bool kin = k < k_end;
+            const int m = m0 + r, n = n0 + r;
+            sxr[kk][r] = (kin && m < Mx) ? x_re[(long long)m * K + k] : 0.0;
+            sxi[kk][r] = (kin && m < Mx) ? x_im[(long long)m * K + k] : 0.0;
+            syr[kk][r] = (kin && n < Ny) ? y_re[(long long)n * K + k] : 0.0;
+            syi[kk][r] = (kin && n < Ny) ? y_im[(long long)n * K + k] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kStep; kk += 4) {
+            double ar[2], ai[2], an[2], br[4], bi[4];
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                ar[a] = sxr[kk + t][16 * wm + 8 * a + g];
+                ai[a] = sxi[kk + t][16 * wm + 8 * a + g];
+                an[a] = -ai[a];
+            }
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                br[b] = syr[kk + t][32 * wn + 8 * b + g];
+                bi[b] = syi[kk + t][32 * wn + 8 * b + g];
+            }
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    dmma(cr[a][b][0], cr[a][b][1], ar[a], br[b]);
+                    dmma(cr[a][b][0], cr[a][b][1], an[a], bi[b]);
+                    dmma(ci[a][b][0], ci[a][b][1], ar[a], bi[b]);
+                    dmma(ci[a][b][0], ci[a][b][1], ai[a], br[b]);
+                }
+        }
+        __syncthreads();
+    }
+    const long long slice = (long long)blockIdx.z * 2 * Mx * Ny;
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int m = m0 + 16 * wm + 8 * a + g, n = n0 + 32 * wn + 8 * b + 2 * t + j;
+                if (m < Mx && n < Ny) {
+                    const long long o = (long long)m * Ny + n;
+                    c_re[slice + o] = cr[a][b][j];
+                    c_im[slice + o] = ci[a][b][j];
+                }
+            }
+}
+
 // C = sum over the K-split slices, in slice order
 __global__ void sum_partials_kernel(const double *__restrict__ part, int split, long long n, double *__restrict__ c_re,
                                     double *__restrict__ c_im)
@@ -140,6 +219,9 @@ __global__ void abs2_kernel(const double *__restrict__ re, const double *__restr
         out[i] = fma(re[i], re[i], im[i] * im[i]);
 }
 
+// which contraction kernel runs: 1 = DMMA (mma.sync.m8n8k4.f64), 0 = the SIMT register-tiled one (rtb_tune "psf_dmma")
+int g_psf_dmma = 1;
+
 // K split so that the grid is at least ~4 waves of blocks (each block still loops over >= 4 k-steps)
 int zgemm_split(int Mx, int Ny, int K, int sm_count, int *k_chunk_out)
 {
@@ -160,18 +242,27 @@ cudaError_t launch_zgemm(int Mx, int Ny, int K, const double *x_re, const double
     const int split = zgemm_split(Mx, Ny, K, sm_count, &k_chunk);
     dim3 grid((Ny + kTile - 1) / kTile, (Mx + kTile - 1) / kTile, split);
     const long long n = (long long)Mx * Ny;
+    const bool tensor = g_psf_dmma != 0;
     if (split == 1) {
-        zgemm_nt_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, c_re, c_im);
+        if (tensor)
+            zgemm_nt_dmma_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, c_re, c_im);
+        else
+            zgemm_nt_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, c_re, c_im);
         if (launches) (*launches)++;
         return cudaGetLastError();
     }
-    zgemm_nt_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, part, part + n);
+    if (tensor)
+        zgemm_nt_dmma_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, part, part + n);
+    else
+        zgemm_nt_kernel<<<grid, 256, 0, stream>>>(Mx, Ny, K, k_chunk, x_re, x_im, y_re, y_im, part, part + n);
     sum_partials_kernel<<<(unsigned)min((long long)sm_count * 8, (n + 255) / 256), 256, 0, stream>>>(part, split, n, c_re, c_im);
     if (launches) (*launches) += 2;
     return cudaGetLastError();
 }
 
 } // namespace
+
+void set_psf_dmma(int on) { g_psf_dmma = on; }
 
 // scratch layout (doubles): [0, 2MG) DFT matrix D (re, im) ; [2MG, 4MG) Wt (re, im) ; [4MG, 4MG + 2MM) the field E when
 // the caller does not take it ; then 2GG for the normalised pupil ; then the K-split partial sums of the larger product

@@ -18,6 +18,7 @@ cudaError_t launch_trace_f64(const TraceParams &P, int sm_count, cudaStream_t st
 cudaError_t launch_trace_fast(const TraceParams &P, int precision, int sm_count, cudaStream_t stream);
 bool lean_eligible(const TraceParams &P);
 void set_lean_min_share_pct(int pct);
+void set_psf_dmma(int on);
 cudaError_t launch_trace_lean(const TraceParams &P, unsigned *counts, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t launch_generate(const DevSource &src, long long n_rays, double *out, int sm_count, cudaStream_t stream);
 cudaError_t launch_reduce_init(const DevReduce &red, int sm_count, cudaStream_t stream);
@@ -503,6 +504,10 @@ int rtb_tune(const char *key, int64_t value)
     if (!key) return fail(RTB_ERR_INVALID, "key is NULL");
     if (strcmp(key, "lean_min_rays") == 0) {
         g_lean_min_rays.store(value, std::memory_order_relaxed);
+        return RTB_OK;
+    }
+    if (strcmp(key, "psf_dmma") == 0) {
+        rtb::set_psf_dmma((int)value);
         return RTB_OK;
     }
     if (strcmp(key, "lean_min_share_pct") == 0) {
