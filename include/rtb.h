@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 4 /* 2: rtb_surface.hints, rtb_measure_dfma_chain_rate; 3: rtb_tune; 4: rtb_comm_* */
+#define RTB_ABI_VERSION 5 /* 2: rtb_surface.hints, rtb_measure_dfma_chain_rate; 3: rtb_tune; 4: rtb_comm_*; 5: rtb_pure_launch_count */
 /* per launch (the prescription travels in the kernel parameter block); the host layer chains longer systems */
 #define RTB_MAX_SURFACES 64
 #define RTB_MAX_WAVELENGTHS 8 /* rows of the host refractive-index table (one extra row answers NaN wavelengths) */
@@ -225,6 +225,8 @@ const char *rtb_last_error(void);
 int rtb_device_count(void);
 /* kernels launched by this library in this process so far (for bench.py's gpu_launches claim) */
 int64_t rtb_launch_count(void);
+/* lean launches so far that ran the pure kernel instantiations (picked by the verdict cache, see rtb_tune "lean_pure") */
+int64_t rtb_pure_launch_count(void);
 
 /*
  * Tuning knobs (never change a result, only which kernel gets there):
@@ -235,6 +237,14 @@ int64_t rtb_launch_count(void);
  *                    surfaces are on-axis spheres / flats, the ones it has lean steps for (RTB_LEAN_MIN_SHARE_PCT).
  *   "psf_dmma"       1 (default): the PSF contraction runs on the FP64 tensor path (mma.sync.m8n8k4.f64); 0: the SIMT
  *                    register-tiled kernel.  Same sums in a different order (agreement ~1e-13 relative).
+ *   "lean_pure"      which lean kernel traces a system whose every surface has a lean step.  1 (default): the "pure"
+ *                    instantiations -- no general steps, control flow from kernel parameters only, the prescription read
+ *                    through the uniform datapath, +4 % -- once the probe of an EARLIER launch of the same system (and,
+ *                    for on-device sources, the same source description) has found no surface where whole bundles fail
+ *                    the lean step; every launch's probe counts are read back asynchronously for the next one, nothing
+ *                    synchronises.  0: the probe-driven kernels always.  2: the pure kernels whatever the bundle (tests).
+ *                    RTB_LEAN_PURE sets the initial value.  A stale verdict costs time only: failing rays are re-traced.
+ *                    Setting the mode forgets every cached verdict.
  *   "keep_probe_counts" test hook: 1 = every lean launch synchronises and keeps its probe's per-surface counts for
  *                    rtb_last_probe_counts().
  *   "host_fail_chunk" test hook: rtb_trace_host returns RTB_ERR_CUDA when it is about to launch chunk n (0-based) of a

@@ -18,7 +18,7 @@ import os
 # RTB_LIBRARY_PATH selects another build of the same library (used to A/B kernel variants on the GPU box)
 LIB_PATH = Path(os.environ.get("RTB_LIBRARY_PATH") or (Path(__file__).resolve().parent / "_lib" / "librtb.so"))
 
-RTB_ABI_VERSION = 4
+RTB_ABI_VERSION = 5
 RTB_COMM_ID_BYTES = 128
 RTB_MAX_SURFACES = 64
 RTB_MAX_WAVELENGTHS = 8
@@ -85,7 +85,7 @@ class RtbError(RuntimeError):
 _lib = None
 
 # every symbol include/rtb.h declares (tests check the .so exports all of them)
-EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_count", "rtb_trace_device",
+EXPORTS = ["rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_launch_count", "rtb_pure_launch_count", "rtb_trace_device",
            "rtb_trace_host", "rtb_trace_source", "rtb_trace_sources", "rtb_generate_device", "rtb_reduce_init",
            "rtb_intersect_rays_device", "rtb_measure_dfma_rate", "rtb_measure_dfma_chain_rate",
            "rtb_measure_copy_bandwidth", "rtb_ray2plane_device", "rtb_distinct_wavelengths_device", "rtb_distinct_wavelengths_host", "rtb_host_alloc", "rtb_host_free",
@@ -108,6 +108,7 @@ def lib():
     L.rtb_last_error.restype = C.c_char_p
     L.rtb_device_count.restype = i32
     L.rtb_launch_count.restype = i64
+    L.rtb_pure_launch_count.restype = i64
     L.rtb_trace_device.argtypes = [C.POINTER(RtbSystem), vp, i64, vp, C.POINTER(RtbTraceOpts), i32, vp]
     L.rtb_trace_host.argtypes = [C.POINTER(RtbSystem), vp, i64, vp, C.POINTER(RtbTraceOpts), i32]
     L.rtb_trace_source.argtypes = [C.POINTER(RtbSystem), C.POINTER(RtbSource), i64, i64, vp,

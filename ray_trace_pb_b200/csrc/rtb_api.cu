@@ -19,7 +19,9 @@ cudaError_t launch_trace_fast(const TraceParams &P, int precision, int sm_count,
 bool lean_eligible(const TraceParams &P);
 void set_lean_min_share_pct(int pct);
 void set_psf_dmma(int on);
-cudaError_t launch_trace_lean(const TraceParams &P, unsigned *counts, int sm_count, cudaStream_t stream, int *launches);
+cudaError_t launch_trace_lean(const TraceParams &P, unsigned *counts, int sm_count, cudaStream_t stream, int *launches,
+                              int pure_mode, unsigned long long verdict_general, bool *pure_used);
+unsigned long long lean_verdict_from_counts(const unsigned *counts, int n_src, int n_surf);
 cudaError_t launch_generate(const DevSource &src, long long n_rays, double *out, int sm_count, cudaStream_t stream);
 cudaError_t launch_reduce_init(const DevReduce &red, int sm_count, cudaStream_t stream);
 cudaError_t launch_intersect(const double *r1, long long n1, const double *r2, long long n2, double *out,
@@ -52,6 +54,11 @@ std::atomic<long long> g_host_fail_chunk{-1};
 // source only) for rtb_last_probe_counts()
 std::atomic<long long> g_keep_probe_counts{0};
 unsigned g_last_probe_counts[2 * RTB_MAX_SURFACES];
+// rtb_tune("lean_pure", m): 0 = the probe-driven lean kernels only; 1 (default) = the pure lean kernels once an earlier
+// probe of the same system and bundle has said that every surface can run its lean step (the verdict cache below);
+// 2 = the pure kernels whenever the system has a lean step for every surface, whatever the bundle (tests).
+std::atomic<long long> g_lean_pure{1};
+std::atomic<long long> g_pure_launches{0};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -99,10 +106,35 @@ struct Slot {
     size_t dev_in_bytes = 0, dev_out_bytes = 0, pin_in_bytes = 0, pin_out_bytes = 0;
 };
 
+// ---- the lean kernel's verdict cache (trace_lean.cu) -------------------------------------------------
+// The pure instantiations of the lean kernel branch on kernel parameters only, so the choice "can every surface of this
+// system run its lean step with this bundle" has to be made on the host before the launch -- but the probe's counts are
+// on the device.  Every lean launch therefore copies its probe's counts to a pinned slot asynchronously (no
+// synchronisation), and the NEXT launch of the same system + bundle description picks its kernel by them.  A wrong verdict
+// costs time, never a bit of the result: rays that fail a lean step are re-traced by redo_ray in every kernel.  A key
+// whose verdict keeps changing (one system traced alternately with bundles of different character from device arrays)
+// stays with the probe-driven kernels.
+constexpr int kVerdictEntries = 16;
+constexpr int kVerdictMaxSources = 64;
+
+struct VerdictEntry {
+    unsigned long long key = 0;
+    bool used = false, have = false, pending = false;
+    unsigned long long general = 0;   // the last consumed probe's verdict (lean_verdict_from_counts)
+    int flips = 0, stable = 0;
+    int pending_n_src = 0, pending_n_surf = 0;
+    unsigned *pin = nullptr;          // kVerdictMaxSources x kMaxSurfaces x 2 counts, page-locked
+    cudaEvent_t ev = nullptr;
+    unsigned long long stamp = 0;
+};
+
 struct DeviceCtx {
     bool ready = false;
     int sm_count = 0;
     Slot slot[kSlots];
+    std::mutex verdict_mutex;
+    VerdictEntry verdict[kVerdictEntries];
+    unsigned long long verdict_clock = 0;
     std::mutex host_path; // one host-buffer trace at a time per device
     cudaMemPool_t pool = nullptr; // small stream-ordered allocations (sweep source lists); keeps its memory
 };
@@ -400,6 +432,7 @@ bool wants_lean(const rtb::TraceParams &P, int precision)
     static const bool env_read = [] {
         if (const char *env = getenv("RTB_LEAN_MIN_RAYS")) g_lean_min_rays.store(atoll(env), std::memory_order_relaxed);
         if (const char *env = getenv("RTB_LEAN_MIN_SHARE_PCT")) rtb::set_lean_min_share_pct(atoi(env));
+        if (const char *env = getenv("RTB_LEAN_PURE")) g_lean_pure.store(std::min(2ll, std::max(0ll, atoll(env))), std::memory_order_relaxed);
         return true;
     }();
     (void)env_read;
@@ -407,13 +440,121 @@ bool wants_lean(const rtb::TraceParams &P, int precision)
     return precision == RTB_F64_EXACT && min_rays >= 0 && P.n_rays >= min_rays && rtb::lean_eligible(P);
 }
 
+// 64-bit mix of a byte range (8 bytes at a time; the tail byte-wise)
+unsigned long long hash_bytes(unsigned long long h, const void *data, size_t n)
+{
+    const unsigned char *p = (const unsigned char *)data;
+    for (; n >= 8; n -= 8, p += 8) {
+        unsigned long long w;
+        memcpy(&w, p, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    for (; n > 0; n--, p++) h = (h ^ *p) * 0x100000001B3ull;
+    return h;
+}
+
+// what a verdict depends on: the prescription, the media / index tables, and the description of the bundle where the
+// library has one (`bundle_key`: on-device sources; rays that arrive as arrays are the caller's business -- see above)
+unsigned long long verdict_key(const rtb::TraceParams &P, unsigned long long bundle_key)
+{
+    unsigned long long h = 0xcbf29ce484222325ull ^ bundle_key;
+    h = hash_bytes(h, &P.n_surf, sizeof(P.n_surf));
+    h = hash_bytes(h, &P.n_wl, sizeof(P.n_wl));
+    h = hash_bytes(h, P.surf, sizeof(rtb::DevSurface) * (size_t)P.n_surf);
+    h = hash_bytes(h, P.mat, sizeof(rtb::DevMaterial) * (size_t)(P.n_surf + 1));
+    if (P.n_wl > 0) {
+        h = hash_bytes(h, P.wl, sizeof(double) * (size_t)P.n_wl);
+        h = hash_bytes(h, P.n_tab, sizeof(double) * (size_t)(P.n_wl + 1) * (size_t)(P.n_surf + 1));
+    }
+    return h ? h : 1ull;
+}
+
+unsigned long long source_key(const rtb::DevSource *list, int n)
+{
+    unsigned long long h = 0x84222325cbf29ce4ull;
+    for (int k = 0; k < n; k++) {
+        rtb::DevSource d = list[k];
+        d.first = 0;                      // (a shard of a source is the same kind of bundle)
+        h = hash_bytes(h, &d, sizeof(d));
+    }
+    return h;
+}
+
+// Consume a finished read-back, then say which kernel this launch should use.  Returns the entry that may take this
+// launch's read-back (NULL: none free, or caching is off).
+VerdictEntry *verdict_lookup(DeviceCtx *ctx, unsigned long long key, int n_src, int *pure_mode, unsigned long long *general)
+{
+    *pure_mode = 0;
+    *general = 0ull;
+    if (n_src > kVerdictMaxSources) return nullptr;
+    VerdictEntry *e = nullptr, *victim = nullptr;
+    for (VerdictEntry &v : ctx->verdict) {
+        if (v.used && v.key == key) {
+            e = &v;
+            break;
+        }
+        // (a slot whose read-back is still in flight keeps its buffer); else: an unused slot, or the least recently used
+        if (v.used && v.pending && cudaEventQuery(v.ev) != cudaSuccess) continue;
+        if (!victim || (victim->used && (!v.used || v.stamp < victim->stamp))) victim = &v;
+    }
+    cudaGetLastError();                   // (cudaErrorNotReady from the queries is not an error)
+    if (!e) {
+        if (!victim) return nullptr;
+        e = victim;
+        unsigned *pin = e->pin;
+        cudaEvent_t ev = e->ev;
+        *e = VerdictEntry();
+        e->pin = pin;
+        e->ev = ev;
+        e->used = true;
+        e->key = key;
+        if (!e->pin && cudaHostAlloc((void **)&e->pin, sizeof(unsigned) * 2 * rtb::kMaxSurfaces * kVerdictMaxSources,
+                                     cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            e->used = false;
+            return nullptr;
+        }
+        if (!e->ev && cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            e->used = false;
+            return nullptr;
+        }
+    }
+    e->stamp = ++ctx->verdict_clock;
+    if (e->pending) {
+        const cudaError_t q = cudaEventQuery(e->ev);
+        if (q == cudaSuccess) {
+            const unsigned long long g = rtb::lean_verdict_from_counts(e->pin, e->pending_n_src, e->pending_n_surf);
+            if (e->have && g != e->general) {
+                e->flips++;
+                e->stable = 0;
+            } else if (++e->stable >= 16) {
+                e->flips = 0;
+            }
+            e->general = g;
+            e->have = true;
+            e->pending = false;
+        } else if (q != cudaErrorNotReady) {
+            e->pending = false;           // (the stream died: forget the read-back)
+        }
+        cudaGetLastError();
+    }
+    if (e->have && e->flips < 3) {
+        *pure_mode = 1;
+        *general = e->general;
+    }
+    return e->pending ? nullptr : e;
+}
+
 // `lean_counts`: probe scratch owned by the caller (the host pipeline's slots), or NULL to take it from the device's
-// stream-ordered pool for the duration of this launch.
+// stream-ordered pool for the duration of this launch.  `bundle_key`: see verdict_key.
 int launch(const rtb::TraceParams &P, int precision, DeviceCtx *ctx, int device, cudaStream_t stream,
-           unsigned *lean_counts = nullptr)
+           unsigned *lean_counts = nullptr, unsigned long long bundle_key = 0ull)
 {
     if (P.n_rays > 0 && wants_lean(P, precision)) {
-        const size_t bytes = sizeof(unsigned) * 2 * rtb::kMaxSurfaces * (size_t)std::max(P.n_src, 1);
+        const int n_src = std::max(P.n_src, 1);
+        const size_t bytes = sizeof(unsigned) * 2 * rtb::kMaxSurfaces * (size_t)n_src;
         unsigned *counts = lean_counts;
         if (!counts) {
             int rc = ensure_pool(ctx, device);
@@ -422,7 +563,40 @@ int launch(const rtb::TraceParams &P, int precision, DeviceCtx *ctx, int device,
                 return fail(RTB_ERR_NOMEM, "stream-ordered allocation of %zu bytes of probe scratch failed", bytes);
         }
         int launches = 0;
-        cudaError_t e = rtb::launch_trace_lean(P, counts, ctx->sm_count, stream, &launches);
+        int pure_mode = (int)g_lean_pure.load(std::memory_order_relaxed);
+        unsigned long long general = 0ull;
+        VerdictEntry *entry = nullptr;
+        std::unique_lock<std::mutex> lock(ctx->verdict_mutex, std::defer_lock);
+        if (pure_mode == 1) {
+            // (a stream that is being captured into a graph can neither be queried nor read back from: no cache)
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+                cudaGetLastError();
+                pure_mode = 0;
+            } else {
+                lock.lock();
+                entry = verdict_lookup(ctx, verdict_key(P, bundle_key), n_src, &pure_mode, &general);
+            }
+        }
+        bool pure_used = false;
+        cudaError_t e = rtb::launch_trace_lean(P, counts, ctx->sm_count, stream, &launches, pure_mode, general, &pure_used);
+        static const bool debug = getenv("RTB_LEAN_DEBUG") != nullptr;
+        if (debug)
+            fprintf(stderr, "[rtb] lean launch: %lld rays x %d src, mode %d, verdict %#llx, entry %p -> %s\n", (long long)P.n_rays,
+                    n_src, pure_mode, general, (void *)entry, pure_used ? "pure" : "probe-driven");
+        if (e == cudaSuccess && entry) {
+            // this launch's probe counts, for the next launch of the same key
+            if (cudaMemcpyAsync(entry->pin, counts, bytes, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+                cudaEventRecord(entry->ev, stream) == cudaSuccess) {
+                entry->pending = true;
+                entry->pending_n_src = n_src;
+                entry->pending_n_surf = P.n_surf;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (lock.owns_lock()) lock.unlock();
+        if (pure_used) g_pure_launches.fetch_add(1, std::memory_order_relaxed);
         if (e == cudaSuccess && g_keep_probe_counts.load(std::memory_order_relaxed))
             e = cudaMemcpyAsync(g_last_probe_counts, counts, sizeof(g_last_probe_counts), cudaMemcpyDeviceToHost, stream),
             cudaStreamSynchronize(stream);
@@ -492,6 +666,8 @@ int rtb_device_count(void)
 
 int64_t rtb_launch_count(void) { return g_launches.load(); }
 
+int64_t rtb_pure_launch_count(void) { return g_pure_launches.load(); }
+
 int rtb_last_probe_counts(uint32_t *out, int n_surfaces)
 {
     if (!out || n_surfaces < 0 || n_surfaces > RTB_MAX_SURFACES) return fail(RTB_ERR_INVALID, "bad arguments");
@@ -512,6 +688,21 @@ int rtb_tune(const char *key, int64_t value)
     }
     if (strcmp(key, "lean_min_share_pct") == 0) {
         rtb::set_lean_min_share_pct((int)value);
+        return RTB_OK;
+    }
+    if (strcmp(key, "lean_pure") == 0) {
+        if (value < 0 || value > 2) return fail(RTB_ERR_INVALID, "lean_pure takes 0, 1 or 2");
+        g_lean_pure.store(value, std::memory_order_relaxed);
+        // (setting the mode also forgets every cached verdict: tests start from a known state)
+        for (DeviceCtx &c : g_ctx) {
+            if (!c.ready) continue;
+            std::lock_guard<std::mutex> lock(c.verdict_mutex);
+            for (VerdictEntry &v : c.verdict) {
+                if (v.used && v.pending) cudaEventSynchronize(v.ev);
+                v.used = v.have = v.pending = false;
+            }
+            cudaGetLastError();
+        }
         return RTB_OK;
     }
     if (strcmp(key, "keep_probe_counts") == 0) {
@@ -561,7 +752,7 @@ int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first
     P.out = out_dev;
     P.n_rays = n_rays;
     P.out_stride = 8 * (long long)n_rays;
-    return launch(P, opts->precision, ctx, device, (cudaStream_t)stream);
+    return launch(P, opts->precision, ctx, device, (cudaStream_t)stream, nullptr, source_key(&P.src, 1));
 }
 
 int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_src, int64_t first_ray,
@@ -604,7 +795,7 @@ int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_s
     P.out = out_dev;
     P.n_rays = n_rays_each;
     P.out_stride = 8 * (long long)n_rays_each * n_src;
-    rc = launch(P, opts->precision, ctx, device, st);
+    rc = launch(P, opts->precision, ctx, device, st, nullptr, source_key(list.data(), n_src));
     cudaFreeAsync(list_dev, st);
     return rc;
 }

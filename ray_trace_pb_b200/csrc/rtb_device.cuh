@@ -121,6 +121,8 @@ struct TraceParams {
     // hot loops' control flow depends on kernel parameters only, which keeps their index in a uniform register
     int32_t lean_n_runs;
     int32_t lean_sample_run;         // the reduction samples after this run (-1: no reduction)
+    int32_t lean_pure;               // the launcher vouches for every surface's lean step: the pure instantiations
+    int32_t lean_pad;
     uint8_t lean_run_end[kMaxSurfaces + 2];
     uint8_t lean_run_code[kMaxSurfaces + 2];
     DevSurface surf[kMaxSurfaces];

@@ -228,7 +228,11 @@ __device__ __forceinline__ bool general_step(const DevSurface &s, int code, doub
 // bucket (rtb_trace_sources).  PROBE: the probe launch -- a strided sample of the rays, per-surface recovery, counts only.
 // KINDS   0: the instantiation for systems of spheres and on-axis flats only (lens trains: the relay, doublets, the
 //            achromat systems) -- it does not carry the perfect-lens, tilted-flat and mirror steps, whose mere presence
-//            costs the sphere loop 2 % through register allocation; 1: every step.
+//            costs the sphere loop 2 % through register allocation; 1: every step.  2 / 3: the PURE forms of 0 / of
+//            "every lean step": no general steps, no probe counts -- the launcher has made sure (from an earlier probe's
+//            verdict on the same system, rtb_api.cu) that every surface can run its lean step.  Nothing in them branches on
+//            a value loaded from memory, which lets ptxas keep the loop indices in uniform registers and read the
+//            prescription through the uniform datapath (operands that cost no operand-port cycle).
 template <bool USE_TABLE, bool FROM_SOURCE, bool SWEEP, bool PROBE, int KINDS>
 __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kernel(const __grid_constant__ TraceParams P,
                                                                                   unsigned *probe_counts)
@@ -265,14 +269,14 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
         // it for the careful path)
         bool general = ((P.lean_general >> k) & 1ull) != 0 ||
                        (!sane && (s.kind == RTB_SURF_SPHERE || s.kind == RTB_SURF_PERFECT_LENS));
-        if (!PROBE && P.lean_counts) {
+        if (!PROBE && KINDS < 2 && P.lean_counts) {
             const unsigned *cnt = P.lean_counts + ((size_t)(SWEEP ? blockIdx.y : 0) * kMaxSurfaces + k) * 2;
             general |= (unsigned long long)cnt[1] * kProbeOneIn > (unsigned long long)cnt[0];
         }
         s_c.surf[k].code = step_code(s, general);
     }
     __syncthreads();
-    for (int run = threadIdx.x; run < P.lean_n_runs; run += blockDim.x) {
+    for (int run = threadIdx.x; KINDS < 2 && run < P.lean_n_runs; run += blockDim.x) {
         bool clean = true;
         for (int k = run > 0 ? P.lean_run_end[run - 1] : 0; k < P.lean_run_end[run]; k++)
             clean &= s_c.surf[k].code == P.lean_run_code[run];
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                 const int end = P.lean_run_end[run];
                 // (a run is "clean" when the probe left every surface of it on the launcher's step)
                 // (an overridden run goes through the loop that dispatches per surface)
-                const int code = s_c.run_clean[run] ? P.lean_run_code[run] : kMixedRun;
+                const int code = (KINDS >= 2 || s_c.run_clean[run]) ? P.lean_run_code[run] : kMixedRun;
                 if (code == kLeanSphere) {
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
@@ -388,7 +392,28 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
-                } else if (KINDS >= 1 && code == kLeanFlatAny) {
+                } else if (KINDS >= 2 && code == kLeanFlatZ) {
+                    // (pure kernels only: the zero-tolerant on-axis flat where the cached verdict asks for it; the
+                    // probe-driven kernels reach this step through their dispatching loop)
+                    for (int k = begin; k < end; k++) {
+                        if (!__any_sync(0xffffffffu, alive)) {
+                            at_valid = false;
+                            break;
+                        }
+                        if (USE_TABLE) {
+                            n1 = pair[0];
+                            pair += 2;
+                        }
+                        const double n2 = USE_TABLE ? 0.0 : eval_index(P.mat[k + 1], wl0);
+                        const double ratio = USE_TABLE ? pair[-1] : xm::div(n1, n2);
+                        bool ok = true, kill;
+                        const bool on = lean::flat_axial<true>(ok, P.surf[k], r, n1, ratio, wl0, wl_rcp, kill);
+                        failed = failed | (alive & !ok);
+                        at_valid = alive & ok & !kill;
+                        alive = alive & ok & on;
+                        if (!USE_TABLE) n1 = n2;
+                    }
+                } else if ((KINDS == 1 || KINDS == 3) && code == kLeanFlatAny) {
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
                             at_valid = false;
@@ -407,7 +432,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
-                } else if (KINDS >= 1 && code == kLeanLens) {
+                } else if ((KINDS == 1 || KINDS == 3) && code == kLeanLens) {
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
                             at_valid = false;
@@ -428,7 +453,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
-                } else if (KINDS >= 1 && code == kGeneralLens) {
+                } else if (KINDS == 1 && code == kGeneralLens) {
                     // a run of perfect lenses: its own loop, so that the hot code of a lens train (the OPM: 4f relays of
                     // perfect lenses and flats) is this step and the flats' -- not every step the kernel knows
                     for (int k = begin; k < end; k++) {
@@ -455,7 +480,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
-                } else if (code == kGeneralRefracting) {
+                } else if (KINDS < 2 && code == kGeneralRefracting) {
                     // tilted / decentred flats and spheres, or ones the launcher keeps off the lean steps
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
@@ -480,7 +505,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                         alive = alive & ok & on;
                         if (!USE_TABLE) n1 = n2;
                     }
-                } else {
+                } else if (KINDS < 2) {
                     for (int k = begin; k < end; k++) {
                         if (!__any_sync(0xffffffffu, alive)) {
                             at_valid = false;      // (the surface that would have been sampled is not reached)
@@ -506,14 +531,14 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
                             on = lean::flat_axial<false>(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
                         } else if (ss.code == kLeanFlatZ) {
                             on = lean::flat_axial<true>(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
-                        } else if (KINDS >= 1 && ss.code == kLeanFlatAny) {
+                        } else if (KINDS == 1 && ss.code == kLeanFlatAny) {
                             on = lean::flat_any(ok, s, r, n1, ratio, wl0, wl_rcp, kill);
-                        } else if (KINDS >= 1 && ss.code == kLeanLens) {
+                        } else if (KINDS == 1 && ss.code == kLeanLens) {
                             on = lean::lens_any(ok, s, ss.rcp, r, n1, n2, wl0, wl_rcp);
                             kill = false;
                         } else {
                             // (KINDS = 0: the launcher has made sure that only refracting surfaces get here)
-                            on = general_step(s, KINDS >= 1 ? ss.code : (int)kGeneralRefracting, ss.rcp, ss.rcp_ok != 0, r, n1,
+                            on = general_step(s, KINDS == 1 ? ss.code : (int)kGeneralRefracting, ss.rcp, ss.rcp_ok != 0, r, n1,
                                               n2, ratio, wl0, wl_rcp, ok, kill);
                         }
                         failed = failed | (alive & !ok);
@@ -619,7 +644,12 @@ cudaError_t launch_lean_one(const TraceParams &P, unsigned blocks, unsigned n_y,
 {
     size_t dyn = T ? 2 * sizeof(double) * (size_t)(P.n_wl + 1) * (size_t)(P.n_surf + 1) : 0;
     if (!PR && P.red.slab >= 0 && P.red.stats) dyn += sizeof(double) * 12 * kLeanThreads;
-    if (!PR && refracting_only(P))
+    const bool pure = !PR && P.lean_pure != 0;
+    if (pure && refracting_only(P))
+        trace_lean_kernel<T, S, W, false, 2><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
+    else if (pure)
+        trace_lean_kernel<T, S, W, false, 3><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
+    else if (!PR && refracting_only(P))
         trace_lean_kernel<T, S, W, PR, 0><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
     else
         trace_lean_kernel<T, S, W, PR, 1><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
@@ -672,10 +702,64 @@ bool lean_eligible(const TraceParams &P)
     return P.n_surf > 0;
 }
 
+// The probe's rule, for the host: bit k is set when more than 1 in kProbeOneIn of the probe rays that reached surface k
+// failed their lean step there, in any source (`counts`: n_src x kMaxSurfaces x {reached, failed}, the probe's output).
+unsigned long long lean_verdict_from_counts(const unsigned *counts, int n_src, int n_surf)
+{
+    unsigned long long general = 0ull;
+    for (int j = 0; j < n_src; j++)
+        for (int k = 0; k < n_surf; k++) {
+            const unsigned *cnt = counts + ((size_t)j * kMaxSurfaces + k) * 2;
+            if ((unsigned long long)cnt[1] * kProbeOneIn > (unsigned long long)cnt[0]) general |= 1ull << k;
+        }
+    return general;
+}
+
+namespace {
+bool sane_reciprocal(const DevSurface &s)
+{
+    const double den = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
+    const bool needs_rcp = s.kind == RTB_SURF_SPHERE || s.kind == RTB_SURF_PERFECT_LENS;
+    return !needs_rcp || (std::isfinite(den) && fabs(den) > 1e-150 && fabs(den) < 4503599627370496.0);
+}
+
+// runs of equal step codes, split where the reduction samples; `general`: surfaces kept off their plain lean step.
+// Returns whether every surface ended up on a lean step.
+bool build_runs(TraceParams &P, unsigned long long general)
+{
+    const int k_red = P.red.slab >= 0 ? (P.red.slab - 1) >> 1 : -1;
+    bool all_lean = P.n_surf > 0;
+    P.lean_n_runs = 0;
+    P.lean_sample_run = -1;
+    int prev = -1;
+    for (int k = 0; k < P.n_surf; k++) {
+        const DevSurface &s = P.surf[k];
+        const int code = step_code(s, ((general >> k) & 1ull) != 0 || !sane_reciprocal(s));
+        all_lean &= code < kGeneralRefracting || code > kMixedRun;
+        if (code != prev) P.lean_n_runs++;
+        P.lean_run_code[P.lean_n_runs - 1] = (uint8_t)code;
+        P.lean_run_end[P.lean_n_runs - 1] = (uint8_t)(k + 1);
+        prev = code;
+        if (k == k_red) {
+            P.lean_sample_run = P.lean_n_runs - 1;
+            prev = -1;
+        }
+    }
+    return all_lean;
+}
+} // namespace
+
 // `counts`: device scratch of n_sources * kMaxSurfaces * 2 unsigned for the probe (zeroed here), owned by the caller for
 // the duration of both launches.  *launches is increased by the number of kernels launched.
-cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_count, cudaStream_t stream, int *launches)
+// `pure_mode` 0: the probe-driven kernels.  1: the pure kernels, if the system allows, with `verdict_general` = the
+// surfaces at which an EARLIER probe of the same system and bundle found bundle-wide failures of the plain lean step
+// (rtb_api.cu's cache; on-axis flats among them run the zero-tolerant lean flat, anything else sends the launch back to the
+// probe-driven kernels).  2: the pure kernels with no verdict (tests: whatever fails is re-traced by redo_ray).  The probe
+// runs in every mode -- in the pure modes its counts only feed the caller's next verdict.  *pure_used says what ran.
+cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_count, cudaStream_t stream, int *launches,
+                              int pure_mode, unsigned long long verdict_general, bool *pure_used)
 {
+    if (pure_used) *pure_used = false;
     if (P_in.n_rays <= 0) return cudaSuccess;
     TraceParams P = P_in;
     const bool sweep = P.n_src > 0;
@@ -686,28 +770,12 @@ cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_
         const DevSurface &s = P.surf[k];
         if (!has_lean_step(s)) P.lean_general |= 1ull << k;
     }
-    // runs of equal step codes, split where the reduction samples
-    {
-        const int k_red = P.red.slab >= 0 ? (P.red.slab - 1) >> 1 : -1;
-        P.lean_n_runs = 0;
-        P.lean_sample_run = -1;
-        int prev = -1;
-        for (int k = 0; k < P.n_surf; k++) {
-            const DevSurface &s = P.surf[k];
-            const double den = (s.kind == RTB_SURF_PERFECT_LENS) ? s.focal_len : s.radius;
-            const bool needs_rcp = s.kind == RTB_SURF_SPHERE || s.kind == RTB_SURF_PERFECT_LENS;
-            const bool sane = std::isfinite(den) && fabs(den) > 1e-150 && fabs(den) < 4503599627370496.0;
-            const int code = step_code(s, ((P.lean_general >> k) & 1ull) != 0 || (needs_rcp && !sane));
-            if (code != prev) P.lean_n_runs++;
-            P.lean_run_code[P.lean_n_runs - 1] = (uint8_t)code;
-            P.lean_run_end[P.lean_n_runs - 1] = (uint8_t)(k + 1);
-            prev = code;
-            if (k == k_red) {
-                P.lean_sample_run = P.lean_n_runs - 1;
-                prev = -1;
-            }
-        }
-    }
+    P.lean_pure = 0;
+    if (pure_mode != 0 && P.lean_general == 0ull && build_runs(P, pure_mode == 1 ? verdict_general : 0ull))
+        P.lean_pure = 1;
+    else
+        build_runs(P, P.lean_general);
+    if (pure_used) *pure_used = P.lean_pure != 0;
     cudaError_t e;
     P.lean_counts = nullptr;
     if (counts) {

@@ -35,11 +35,15 @@ def dev():
     return dev
 
 
-@pytest.fixture()
-def lean():
-    """every eligible launch goes to the lean kernel for the duration of the test; `lean.off()` / `lean.on()` switch"""
+@pytest.fixture(params=["probe_driven", "pure"])
+def lean(request):
+    """every eligible launch goes to the lean kernel for the duration of the test; `lean.off()` / `lean.on()` switch.
+    Run twice: with the probe-driven kernels only (rtb_tune "lean_pure" = 0), and with the pure instantiations forced on
+    for every system that has a lean step for each surface, whatever the bundle (= 2: no verdict, so bundles that the
+    plain lean steps cannot take -- sources on a flat, beams along its normal -- go ray by ray through redo_ray)."""
     from ray_trace_pb_b200 import _ffi
     L = _ffi.lib()
+    _ffi.check(L.rtb_tune(b"lean_pure", 2 if request.param == "pure" else 0))
 
     class Switch:
         @staticmethod
@@ -61,6 +65,7 @@ def lean():
     yield Switch
     _ffi.check(L.rtb_tune(b"keep_probe_counts", 0))
     _ffi.check(L.rtb_tune(b"lean_min_rays", 32768))
+    _ffi.check(L.rtb_tune(b"lean_pure", 1))
 
 
 # ------------------------------------------------------------------------------------------------ reference pins
@@ -235,3 +240,91 @@ def test_probe_finds_the_surfaces_that_need_zero_forms(rt, rtm, dev, torch, lean
     counts = lean.probe_counts(len(system.surfaces))
     assert counts[0, 1] == counts[0, 0] > 1500, counts
     assert (counts[1:, 1] * 50 <= counts[1:, 0]).all(), counts
+
+
+# ------------------------------------------------------------------------------------------------ the verdict cache
+@pytest.fixture()
+def cache():
+    """the default mode (rtb_tune "lean_pure" = 1) with the lean kernel taking every eligible launch"""
+    from ray_trace_pb_b200 import _ffi
+    L = _ffi.lib()
+    _ffi.check(L.rtb_tune(b"lean_pure", 1))
+    _ffi.check(L.rtb_tune(b"lean_min_rays", 0))
+    yield L.rtb_pure_launch_count
+    _ffi.check(L.rtb_tune(b"lean_min_rays", 32768))
+
+
+def test_verdict_cache_picks_the_pure_kernel_from_the_second_launch(rt, rtm, oracle, dev, torch, cache):
+    """launch 1 of a system: probe-driven kernel, its probe's counts are read back asynchronously; launches 2.. : the pure
+    kernel.  Same bits from both, and from the oracle."""
+    system = systems.relay10_system(rt, rtm)
+    vac = rtm.Vacuum()
+    mats = [vac] + list(system.materials) + [vac]
+    rays = _fuzz(50_000, 11, spread=0.03)
+    surfaces = list(system.surfaces)        # (the `cache` fixture has emptied the cache)
+    want = oracle.ray_trace(system, rays, vac, vac, n_threads=8)[-1:]
+    d_rays = torch.from_numpy(rays).cuda()
+    outs, pure = [], []
+    for _ in range(4):
+        before = cache()
+        out = dev.trace_tensor(surfaces, mats, d_rays, keep="last", wavelengths=[0.785])
+        torch.cuda.synchronize()
+        pure.append(cache() - before)
+        outs.append(out.cpu().numpy())
+    assert pure == [0, 1, 1, 1], pure
+    for o in outs:
+        parity.assert_bit_identical(o, want, "relay, verdict cache")
+
+
+def test_verdict_cache_zero_tolerant_flat_and_changing_bundles(rt, rtm, oracle, dev, torch, cache):
+    """config 1's plano-convex lens: the beam runs along the first flat's normal, so the cached verdict puts the
+    zero-tolerant lean flat into the pure kernel's runs; then the same system under bundles of another character (a
+    skew fan, for which the verdict is stale: whatever fails is re-traced) -- always the oracle's bits; a key whose
+    verdict keeps changing ends up with the probe-driven kernels."""
+    system, m_in, m_out, _ = systems.plano_convex(rt, rtm)
+    mats = [m_in] + list(system.materials) + [m_out]
+    wl = 0.5
+    along = systems.lattice_rays(200, 8.0, -5.0, wl)
+    skew = _fuzz(40_000, 12, spread=0.02, half=8.0, z0=-5.0, wavelengths=(wl,))
+    want = {"along": oracle.ray_trace(system, along, m_in, m_out, n_threads=8)[-1:],
+            "skew": oracle.ray_trace(system, skew, m_in, m_out, n_threads=8)[-1:]}
+    d = {"along": torch.from_numpy(along).cuda(), "skew": torch.from_numpy(skew).cuda()}
+
+    def run(which):
+        before = cache()
+        out = dev.trace_tensor(system.surfaces, mats, d[which], keep="last", wavelengths=[wl])
+        torch.cuda.synchronize()
+        parity.assert_bit_identical(out.cpu().numpy(), want[which], f"plano-convex, {which} bundle")
+        return cache() - before
+
+    used = [run("along") for _ in range(3)]
+    assert used == [0, 1, 1], used           # pure from the second launch on, with the zero-tolerant flat
+    # alternate the bundles: every launch's verdict is the other bundle's; after three changes the key is left alone
+    used = [run("skew" if k % 2 == 0 else "along") for k in range(10)]
+    assert used[-3:] == [0, 0, 0], used
+
+
+def test_verdict_cache_sources_and_sweeps(rt, rtm, dev, torch, cache):
+    """on-device sources carry their description into the key: a sweep's verdict is its own"""
+    system = systems.relay10_system(rt, rtm)
+    vac = rtm.Vacuum()
+    mats = [vac] + list(system.materials) + [vac]
+    # (fields off both coordinate planes: a beam tilted about y alone keeps its y = 0 row of rays in the meridional
+    # plane, exact zeros at every surface -- 151 of 151^2 rays, above the probe's 1-in-200 threshold)
+    thetas = np.linspace(0.001, np.pi / 180, 4)
+    sources = [dev.RaySource.grid([0, 0, 0], 12.0, 151, 0.785, normal=(0.6 * np.sin(t), 0.8 * np.sin(t), np.cos(t)))
+               for t in thetas]
+    outs, used = [], []
+    for _ in range(3):
+        before = cache()
+        red = dev.Reducer(20, buckets=len(sources), grid_n=32, half_width=12.0)
+        out = dev.trace_sources(system.surfaces, mats, sources, keep="last", reducer=red)
+        torch.cuda.synchronize()
+        used.append(cache() - before)
+        outs.append((out.cpu().numpy(), red.stats_t.cpu().numpy(), red.grid.cpu().numpy()))
+    assert used == [0, 1, 1], used
+    for o, s, g in outs[1:]:
+        parity.assert_bit_identical(o, outs[0][0], "sweep, pure vs probe-driven")
+        assert (s[:, 0] == outs[0][1][:, 0]).all()
+        np.testing.assert_allclose(s[:, 1:8], outs[0][1][:, 1:8], rtol=1e-10, atol=1e-6)
+        np.testing.assert_array_equal(g[:, 2], outs[0][2][:, 2])
