@@ -362,6 +362,7 @@ int pack_params(const rtb_system *sys, const rtb_trace_opts *opts, rtb::TracePar
         d.stats = r.stats_dev;
         d.grid = r.grid_n > 0 ? r.grid_dev : nullptr;
         if (!d.stats && !d.grid) d.slab = -1;
+        rtb::finish_reduce(d);
     }
     for (int k = 0; k < S; k++) {
         int act = 0;
@@ -884,7 +885,20 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
         drain();
         return fail(RTB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
     };
+    // RTB_HOST_TIMELINE=1: per-chunk timestamps (copy-in start / end, kernels end, copy-out end) on stderr after the call
+    // (diagnostics: the timing events themselves cost the pipeline ~15 %)
+    static const bool timeline = getenv("RTB_HOST_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> marks;
+    auto mark = [&](cudaStream_t st) {
+        if (!timeline) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        marks.push_back(ev);
+    };
     auto run_pipeline = [&]() -> int {
+        // (equal chunks: ones that taper towards both ends of the call -- to shrink the copy-in and copy-out that have
+        // nothing to overlap with -- were measured twice, rounds 1 and 2, and change nothing: DESIGN.md section 8)
         const long long n_chunks = (n_rays + chunk - 1) / chunk;
         for (long long c = 0; c < n_chunks; c++) {
             const int s = (int)(c % kSlots);
@@ -897,9 +911,11 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
                 memcpy(sl.pin_in, src, (size_t)cnt * row);
                 src = sl.pin_in;
             }
+            mark(sl.stream);
             if ((rc = cuda_failed(cudaMemcpyAsync(sl.dev_in, src, (size_t)cnt * row, cudaMemcpyHostToDevice, sl.stream),
                                   "copy-in")))
                 return rc;
+            mark(sl.stream);
             P.rays_in = sl.dev_in;
             P.out = sl.dev_out;
             P.n_rays = cnt;
@@ -907,6 +923,7 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
             if (c == g_host_fail_chunk.load(std::memory_order_relaxed))
                 return fail(RTB_ERR_CUDA, "injected failure before the launch of chunk %lld (rtb_tune host_fail_chunk)", c);
             if ((rc = launch(P, opts->precision, ctx, device, sl.stream, sl.lean_counts))) return rc;
+            mark(sl.stream);
             if (slabs > 0) {
                 cudaError_t e = cudaSuccess;
                 if (!out_pinned) {
@@ -922,6 +939,7 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
                 }
                 if ((rc = cuda_failed(e, "copy-out"))) return rc;
             }
+            mark(sl.stream);
             if ((rc = cuda_failed(cudaEventRecord(sl.done, sl.stream), "cudaEventRecord"))) return rc;
             pending[s].active = true;
             pending[s].r0 = r0;
@@ -934,6 +952,20 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
     };
     rc = run_pipeline();
     if (rc) drain();
+    if (timeline && !marks.empty()) {
+        drain();
+        for (size_t k = 0; k + 3 < marks.size(); k += 4) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, marks[0], marks[k]);
+            cudaEventElapsedTime(&b, marks[0], marks[k + 1]);
+            cudaEventElapsedTime(&c, marks[0], marks[k + 2]);
+            cudaEventElapsedTime(&d, marks[0], marks[k + 3]);
+            fprintf(stderr, "[rtb] chunk %3zu: copy-in %8.3f - %8.3f ms, kernels done %8.3f, copy-out done %8.3f\n", k / 4, a, b,
+                    c, d);
+        }
+        for (cudaEvent_t ev : marks) cudaEventDestroy(ev);
+        cudaGetLastError();
+    }
     return rc;
 }
 
@@ -968,6 +1000,7 @@ int rtb_reduce_init(const rtb_reduce *red, int device, void *stream)
     d.stats = red->stats_dev;
     d.grid = red->grid_n > 0 ? red->grid_dev : nullptr;
     d.grid_n = red->grid_n;
+    rtb::finish_reduce(d);
     if (!d.stats && !d.grid) return RTB_OK;
     cudaError_t e = rtb::launch_reduce_init(d, ctx->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "reduce-init launch failed: %s", cudaGetErrorString(e));

@@ -73,7 +73,19 @@ struct DevReduce {
     double *grid;
     int32_t slab; // -1 = no reduction
     int32_t grid_n;
+    // derived (finish_reduce): the sin and count planes of the grid, grid_n as a double
+    double *grid_sin;
+    double *grid_count;
+    double grid_n_f;
 };
+
+__host__ __device__ inline void finish_reduce(DevReduce &r)
+{
+    const long long plane = (long long)r.grid_n * r.grid_n;
+    r.grid_sin = r.grid ? r.grid + plane : nullptr;
+    r.grid_count = r.grid ? r.grid + 2 * plane : nullptr;
+    r.grid_n_f = (double)r.grid_n;
+}
 
 struct DevSource {
     double a_start, a_step, a_stop; // linspace pieces: value(i) = i*a_step + a_start, last forced to a_stop

@@ -143,6 +143,7 @@ __device__ __forceinline__ void sweep_setup(const TraceParams &P, SweepShared<tr
         s.red = P.red;
         if (s.red.stats) s.red.stats += (long long)blockIdx.y * RTB_N_STATS;
         if (s.red.grid) s.red.grid += (long long)blockIdx.y * 3 * s.red.grid_n * s.red.grid_n;
+        finish_reduce(s.red);
     }
 }
 

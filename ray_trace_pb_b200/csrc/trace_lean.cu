@@ -127,7 +127,10 @@ static __device__ __noinline__ void redo_ray(const TraceParams *P, Ray cur, int 
 }
 
 // ---- fused reductions: rtb_reduce in rtb.h (same arithmetic as reduce_sample in trace_common.cuh) --------------------
-// the per-thread tally lives in shared memory, [statistic][thread]
+// The per-thread tally lives in shared memory as six (statistic 2j, statistic 2j + 1) pairs, [pair][thread]: one 128-bit
+// load and store per pair.  u, v and the phase are finite where it is touched, so the extrema are plain compares (fmin /
+// fmax would carry their NaN handling), the cell is the truncation of a non-negative number (floor(x) >= 0 <=> x >= 0,
+// floor(x) < G <=> x < G for an integer G) and fits 32 bits (G <= 32768).
 __device__ __forceinline__ void accumulate(const DevReduce &R, double ox, double oy, double oz, double phase, double *tally)
 {
     const double px = ox - R.ox, py = oy - R.oy, pz = oz - R.oz;
@@ -136,45 +139,48 @@ __device__ __forceinline__ void accumulate(const DevReduce &R, double ox, double
     const double ph = phase - R.phase_ref;
     if (!(isfinite(u) && isfinite(v) && isfinite(ph))) return;
     if (R.stats) {
-        double *t = tally + threadIdx.x;
+        double2 *t = reinterpret_cast<double2 *>(tally) + threadIdx.x;
         constexpr int W = kLeanThreads;
-        t[0 * W] += 1.0;
-        t[1 * W] += u;
-        t[2 * W] += v;
-        t[3 * W] += u * u;
-        t[4 * W] += v * v;
-        t[5 * W] += u * v;
-        t[6 * W] += ph;
-        t[7 * W] += ph * ph;
-        t[8 * W] = fmin(t[8 * W], u);
-        t[9 * W] = fmax(t[9 * W], u);
-        t[10 * W] = fmin(t[10 * W], v);
-        t[11 * W] = fmax(t[11 * W], v);
+        double2 a = t[0 * W], b = t[1 * W], c = t[2 * W], d = t[3 * W], e = t[4 * W], f = t[5 * W];
+        a.x += 1.0;
+        a.y += u;
+        b.x += v;
+        b.y += u * u;
+        c.x += v * v;
+        c.y += u * v;
+        d.x += ph;
+        d.y += ph * ph;
+        e.x = u < e.x ? u : e.x;
+        e.y = u > e.y ? u : e.y;
+        f.x = v < f.x ? v : f.x;
+        f.y = v > f.y ? v : f.y;
+        t[0 * W] = a; t[1 * W] = b; t[2 * W] = c; t[3 * W] = d; t[4 * W] = e; t[5 * W] = f;
     }
     if (R.grid) {
-        const double fu = floor((u + R.half_width) * R.inv_cell);
-        const double fv = floor((v + R.half_width) * R.inv_cell);
-        const double g = (double)R.grid_n;
-        if (fu >= 0.0 && fu < g && fv >= 0.0 && fv < g) {
-            const long long cell = (long long)fv * R.grid_n + (long long)fu;
-            const long long plane = (long long)R.grid_n * R.grid_n;
+        const double xu = (u + R.half_width) * R.inv_cell;
+        const double xv = (v + R.half_width) * R.inv_cell;
+        const double g = R.grid_n_f;
+        if (xu >= 0.0 && xu < g && xv >= 0.0 && xv < g) {
+            const unsigned cell = (unsigned)__double2int_rz(xv) * (unsigned)R.grid_n + (unsigned)__double2int_rz(xu);
             double s, c;
             sincos(ph, &s, &c);
             asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + cell), "d"(c) : "memory");
-            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + plane + cell), "d"(s) : "memory");
-            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid + 2 * plane + cell), "d"(1.0) : "memory");
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid_sin + cell), "d"(s) : "memory");
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(R.grid_count + cell), "d"(1.0) : "memory");
         }
     }
 }
+
+// statistic k of thread `thread` in that layout
+__device__ __forceinline__ int tally_index(int k, int thread) { return ((k >> 1) * kLeanThreads + thread) * 2 + (k & 1); }
 
 __device__ __noinline__ void flush_tally(const DevReduce &R, const double *tally)
 {
     if (!R.stats) return;
     __shared__ double part[12][kLeanThreads / 32];
-    constexpr int W = kLeanThreads;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = 0; k < 12; k++) {
-        double x = tally[k * W + threadIdx.x];
+        double x = tally[tally_index(k, threadIdx.x)];
         x = (k < 8) ? warp_sum(x) : ((k == 8 || k == 10) ? warp_min(x) : warp_max(x));
         if (lane == 0) part[k][warp] = x;
     }
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
 {
     static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
     // dynamic shared memory: {n, n1/n2} pairs per (wavelength row, surface), then the per-thread tallies
-    extern __shared__ double s_dyn[];
+    extern __shared__ __align__(16) double s_dyn[];
     const int n_med = P.n_surf + 1;
     double *const s_pair = s_dyn;
     double *const s_tally = s_dyn + (USE_TABLE ? 2 * (P.n_wl + 1) * n_med : 0);
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
     const bool reducing = !PROBE && P.red.slab >= 0;
     if (reducing && P.red.stats) {
         for (int k = 0; k < 12; k++)
-            s_tally[k * kLeanThreads + threadIdx.x] = (k < 8) ? 0.0 : ((k == 8 || k == 10) ? CUDART_INF : -CUDART_INF);
+            s_tally[tally_index(k, threadIdx.x)] = (k < 8) ? 0.0 : ((k == 8 || k == 10) ? CUDART_INF : -CUDART_INF);
     }
     for (int k = threadIdx.x; k < P.n_surf; k += blockDim.x) {
         const DevSurface &s = P.surf[k];
@@ -616,12 +622,14 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanMinBlocks) trace_lean_kerne
         if (!alive) set_nan(out);
         if (failed) {
             // start over from the launch state (reloaded: it was not kept in registers)
-            Ray launch, sample;
+            // (`redone`, not `out`, goes to the call: a row whose address is taken lives in local memory, for every ray)
+            Ray launch, sample, redone;
             if (FROM_SOURCE)
                 launch = make_ray(source, source.first + i);
             else
                 load_ray(P.rays_in, i, P.n_rays, planes_in, launch);
-            redo_ray<USE_TABLE>(&P, launch, k_red, sample_at, &out, &sample);
+            redo_ray<USE_TABLE>(&P, launch, k_red, sample_at, &redone, &sample);
+            out = redone;
             if (reducing && !sampled) accumulate(red, sample.ox, sample.oy, sample.oz, sample.ph, s_tally);
         }
         if (valid && P.any_store) store_ray(P.out, row0 + i, out_rows, planes_out, out);

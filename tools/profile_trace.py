@@ -19,6 +19,7 @@ ap.add_argument("--keep", default="last")
 ap.add_argument("--reduce", default="none")
 ap.add_argument("--precision", default="f64")
 ap.add_argument("--layout", default="rows")
+ap.add_argument("--sync", action="store_true", help="synchronise after every launch (the verdict cache then has launch 1's probe counts for launch 2: pure kernels)")
 args = ap.parse_args()
 
 system, materials = bench.relay_system()
@@ -36,6 +37,8 @@ for i in range(args.launches):
     out = dev.trace_tensor(system.surfaces, materials, rays, keep=keep, wavelengths=[bench.WAVELENGTH],
                            reducer=reducer, precision=args.precision, layout=args.layout)
     ev[i + 1].record()
+    if args.sync:
+        torch.cuda.synchronize()
 torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.launches)]
 n = rays.shape[1] if args.layout == "planes" else rays.shape[0]
