@@ -146,7 +146,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", type=int, nargs="*", default=[1, 2, 3, 4, 5])
     ap.add_argument("--precision", default="f64")
+    ap.add_argument("--repeat", type=int, default=1, help="run every config this many times (from the second run on the "
+                    "lean kernel's verdict cache picks the pure instantiations)")
     args = ap.parse_args()
     print(f"device: {torch.cuda.get_device_name(0)}; precision {args.precision}")
     for c in args.configs:
-        {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}[c](args.precision)
+        for _ in range(args.repeat):
+            {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}[c](args.precision)
