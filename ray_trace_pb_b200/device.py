@@ -69,7 +69,7 @@ def _system_for(surfaces, materials, wavelengths):
             wavelengths = None
     if wavelengths is None and any(engine.pack_material(m).kind == _ffi.MAT_TABLE_ONLY for m in materials):
         wavelengths = np.array([1.0])   # batch without a valid wavelength: only the NaN row is ever used
-    return engine.pack_system(surfaces, materials, wavelengths)
+    return engine.pack_system_memo(surfaces, materials, wavelengths)
 
 
 def trace_tensor(surfaces, materials, rays, keep="all", precision="f64", wavelengths="auto", reducer=None,

@@ -224,6 +224,60 @@ def pack_system(surfaces, materials, wavelengths=None) -> PackedSystem:
     return PackedSystem(sys, S, keep)
 
 
+# Packing costs ~50 us per surface in Python, which is what a small launch is made of (1e6 rays x 3 surfaces trace in 45
+# us).  Systems that are traced again and again -- sweeps, auto-focus iterations, benchmark loops -- come out of a small
+# memo keyed by VALUE: the surface and material objects stay mutable, as in the reference, and a changed attribute is a
+# different key.  Media that exist only as Python code (their table is whatever n() returns today) are never memoized.
+_PACK_MEMO: "dict[tuple, PackedSystem]" = {}
+_PACK_MEMO_SIZE = 32
+_VECTOR_FIELDS = ("center", "normal", "input_axis", "normal_f")
+
+
+def _surface_key(s):
+    rec = getattr(s, "device_record", None)
+    if rec is None:
+        return None
+    d = rec()
+    key = [type(s)]
+    for name, value in d.items():
+        key.append(np.asarray(value, dtype=np.float64).tobytes() if name in _VECTOR_FIELDS else value)
+    return tuple(key)
+
+
+def _material_key(m):
+    rec = getattr(m, "device_record", None)
+    if rec is None:
+        return None
+    kind, b, c, n_const = rec()
+    if kind == KIND_TABLE_ONLY:
+        return None
+    # (NaN never equals itself: keyed by bit pattern)
+    return (type(m), kind, tuple(b), tuple(c), np.float64(n_const).tobytes())
+
+
+def pack_system_memo(surfaces, materials, wavelengths=None) -> PackedSystem:
+    """pack_system, memoized by the values it would pack (see above).  The returned object is shared between calls:
+    callers may set surface hints on it before each launch, nothing else."""
+    try:
+        key = (tuple(_surface_key(s) for s in surfaces), tuple(_material_key(m) for m in materials),
+               None if wavelengths is None else np.ascontiguousarray(wavelengths, dtype=np.float64).tobytes())
+        if any(k is None for k in key[0]) or any(k is None for k in key[1]):
+            key = None
+        else:
+            hash(key)
+    except Exception:
+        key = None          # anything unusual goes the plain way (and raises there what it has to raise)
+    if key is None:
+        return pack_system(surfaces, materials, wavelengths)
+    hit = _PACK_MEMO.pop(key, None)
+    if hit is None:
+        hit = pack_system(surfaces, materials, wavelengths)
+        while len(_PACK_MEMO) >= _PACK_MEMO_SIZE:
+            _PACK_MEMO.pop(next(iter(_PACK_MEMO)))
+    _PACK_MEMO[key] = hit       # (re-inserted: most recently used last)
+    return hit
+
+
 def resolve_keep(keep, n_slabs: int):
     """-> (keep_mode, int32 array or None, n_out_slabs)"""
     if isinstance(keep, str):
@@ -396,7 +450,7 @@ def trace_host(surfaces, materials, rays: np.ndarray, keep="all", precision="f64
     uniq = choose_wavelength_table(materials, rays)
     if uniq is None and any(pack_material(m).kind == KIND_TABLE_ONLY for m in materials):
         return _trace_host_grouped(surfaces, materials, rays, keep, precision, device, reduce, out)
-    packed = pack_system(surfaces, materials, uniq)
+    packed = pack_system_memo(surfaces, materials, uniq)
     if n:
         sample = rays[np.linspace(0, n - 1, num=min(n, 64)).astype(np.int64)]
         set_first_surface_hint(packed, degenerate_first_surface(surfaces, rays=sample))

@@ -371,3 +371,46 @@ def test_degenerate_first_surface_detection(rt, rtm):
     engine.set_first_surface_hint(packed, False)
     assert packed.sys.surfaces[0].hints == 0
 
+
+
+def test_pack_memo_is_keyed_by_value(rt, rtm):
+    """engine.pack_system_memo: the same prescription comes out of the memo, a changed attribute is a different key (the
+    surface objects stay mutable, as in the reference), media that only exist as Python code are packed afresh"""
+    from ray_trace_pb_b200 import engine
+    system = systems.relay10_system(rt, rtm)
+    vac = rtm.Vacuum()
+    mats = [vac] + list(system.materials) + [vac]
+    a = engine.pack_system_memo(system.surfaces, mats, [0.785])
+    assert engine.pack_system_memo(system.surfaces, mats, [0.785]) is a
+    assert engine.pack_system_memo(system.surfaces, mats, [0.532]) is not a
+    assert engine.pack_system_memo(system.surfaces, mats, None) is not a
+    rebuilt = systems.relay10_system(rt, rtm)                          # other objects, same values
+    assert engine.pack_system_memo(rebuilt.surfaces, [vac] + list(rebuilt.materials) + [vac], [0.785]) is a
+    system.surfaces[3].center = system.surfaces[3].center + np.array([0.0, 0.0, 1e-9])
+    b = engine.pack_system_memo(system.surfaces, mats, [0.785])
+    assert b is not a and b.sys.surfaces[3].center[2] != a.sys.surfaces[3].center[2]
+    system.surfaces[0].aperture_rad = 20.0
+    c = engine.pack_system_memo(system.surfaces, mats, [0.785])
+    assert c is not b and c.sys.surfaces[0].aperture_rad == 20.0
+    mats[2] = rtm.Constant(1.7)
+    d = engine.pack_system_memo(system.surfaces, mats, [0.785])
+    assert d is not c and d.sys.materials[2].n_const == 1.7
+    # byte for byte what the plain packer produces
+    plain = engine.pack_system(system.surfaces, mats, [0.785])
+    for k in range(len(system.surfaces)):
+        assert bytes(d.sys.surfaces[k]) == bytes(plain.sys.surfaces[k])
+
+    class Cauchy:                                                       # a medium that is only Python code
+        def n(self, wl):
+            return 1.5 + 0.004 / np.asarray(wl, dtype=float) ** 2
+
+    flat = rt.FlatSurface([0, 0, 0], [0, 0, 1], 5.0)
+    x = engine.pack_system_memo([flat], [Cauchy(), vac], [0.5])
+    assert engine.pack_system_memo([flat], [Cauchy(), vac], [0.5]) is not x
+
+    class BentFlat(rt.FlatSurface):
+        def propagate(self, rays, n1, n2):
+            return rays
+
+    with pytest.raises(NotImplementedError):
+        engine.pack_system_memo([BentFlat([0, 0, 0], [0, 0, 1], 1.0)], [vac, vac], [0.5])
