@@ -653,6 +653,20 @@ cudaError_t launch_lean_one(const TraceParams &P, unsigned blocks, unsigned n_y,
     size_t dyn = T ? 2 * sizeof(double) * (size_t)(P.n_wl + 1) * (size_t)(P.n_surf + 1) : 0;
     if (!PR && P.red.slab >= 0 && P.red.stats) dyn += sizeof(double) * 12 * kLeanThreads;
     const bool pure = !PR && P.lean_pure != 0;
+    // With lazy module loading (the CUDA default) a kernel is loaded at its first launch, which stalls the host for
+    // milliseconds with the GPU idle -- and the verdict cache launches the pure instantiations for the first time in the
+    // middle of a run of launches.  Load the whole family when its first member is launched.
+    static const bool loaded = [] {
+        cudaFuncAttributes a;
+        cudaFuncGetAttributes(&a, trace_lean_kernel<T, S, W, false, 0>);
+        cudaFuncGetAttributes(&a, trace_lean_kernel<T, S, W, false, 1>);
+        cudaFuncGetAttributes(&a, trace_lean_kernel<T, S, W, false, 2>);
+        cudaFuncGetAttributes(&a, trace_lean_kernel<T, S, W, false, 3>);
+        cudaFuncGetAttributes(&a, trace_lean_kernel<T, S, W, true, 1>);
+        cudaGetLastError();
+        return true;
+    }();
+    (void)loaded;
     if (pure && refracting_only(P))
         trace_lean_kernel<T, S, W, false, 2><<<dim3(blocks, n_y), kLeanThreads, dyn, stream>>>(P, probe_counts);
     else if (pure)
