@@ -93,11 +93,12 @@ namespace {
     } while (0)
 
 // ---- per-device context: SM count, streams and staging buffers of the host pipeline ------------------------
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t copied_in = nullptr;   // this slot's copy-in has landed (the previous chunk's copy-out waits for it)
     unsigned *lean_counts = nullptr;   // probe scratch of the lean kernel for this slot's chunks
     double *dev_in = nullptr;
     double *dev_out = nullptr;
@@ -636,6 +637,13 @@ int grow_pin(double **p, size_t *have, size_t want)
     return RTB_OK;
 }
 
+// RTB_HOST_LAG=0: the host pipeline without the lagged copy-out (see rtb_trace_host)
+bool lag_default()
+{
+    static const bool lag = !(getenv("RTB_HOST_LAG") && atoi(getenv("RTB_HOST_LAG")) == 0);
+    return lag;
+}
+
 bool is_pinned(const void *p)
 {
     cudaPointerAttributes a;
@@ -823,7 +831,7 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
     // chunk so that one chunk's output is ~64 MiB (RTB_HOST_CHUNK_MIB overrides; 8-128 MiB measured within 15%): big enough for PCIe efficiency,
     // small enough that the un-overlapped first copy-in and last copy-out stay a few per cent of the call
     const size_t row = 64;
-    size_t target = (size_t)64 << 20;
+    size_t target = (size_t)(slabs <= 1 && lag_default() ? 16 : 64) << 20;
     if (const char *env = getenv("RTB_HOST_CHUNK_MIB")) {
         const long v = atol(env);
         if (v >= 1 && v <= 4096) target = (size_t)v << 20;
@@ -841,6 +849,7 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
         Slot &sl = ctx->slot[s];
         if (!sl.stream) RTB_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         if (!sl.done) RTB_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        if (!sl.copied_in) RTB_CUDA(cudaEventCreateWithFlags(&sl.copied_in, cudaEventDisableTiming));
         if (!sl.lean_counts) RTB_CUDA(cudaMalloc((void **)&sl.lean_counts, sizeof(unsigned) * 2 * rtb::kMaxSurfaces));
         if ((rc = grow_dev(&sl.dev_in, &sl.dev_in_bytes, (size_t)chunk * row))) return rc;
         if (slabs > 0 && (rc = grow_dev(&sl.dev_out, &sl.dev_out_bytes, (size_t)chunk * row * slabs))) return rc;
@@ -885,16 +894,37 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
         drain();
         return fail(RTB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
     };
-    // RTB_HOST_TIMELINE=1: per-chunk timestamps (copy-in start / end, kernels end, copy-out end) on stderr after the call
-    // (diagnostics: the timing events themselves cost the pipeline ~15 %)
-    static const bool timeline = getenv("RTB_HOST_TIMELINE") != nullptr;
-    std::vector<cudaEvent_t> marks;
-    auto mark = [&](cudaStream_t st) {
-        if (!timeline) return;
-        cudaEvent_t ev;
-        cudaEventCreate(&ev);
-        cudaEventRecord(ev, st);
-        marks.push_back(ev);
+    // The copy-out of chunk c is issued BEHIND THE COPY-IN OF CHUNK c + 1 (an event wait on its own stream): a chunk's two
+    // copies then no longer meet through the compute engine at every step -- the copy-out engine always has a finished
+    // chunk waiting when it ends one, instead of idling through the next chunk's kernels (tools/ubench/copy_pipeline.cu
+    // <chunk> <streams> 1 1 0 <lag>: 16 MiB chunks on 4 streams 24.15 -> 22.75 ms per 2 GiB, the rate of the same pipeline
+    // WITHOUT kernels; RTB_HOST_LAG=0 switches it off).
+    const bool lag = lag_default();
+    auto copy_out = [&](long long c) -> int {
+        const int s = (int)(c % kSlots);
+        Slot &sl = ctx->slot[s];
+        const long long r0 = c * chunk;
+        const long long cnt = std::min<long long>(chunk, n_rays - r0);
+        if (slabs > 0) {
+            cudaError_t e = cudaSuccess;
+            if (!out_pinned) {
+                e = cudaMemcpyAsync(sl.pin_out, sl.dev_out, (size_t)cnt * row * slabs, cudaMemcpyDeviceToHost, sl.stream);
+            } else if (strided_copy_ok) {
+                // (slabs, cnt, 8) device -> rows [r0, r0+cnt) of every slab of the (slabs, N, 8) host array
+                e = cudaMemcpy2DAsync(out_host + (size_t)r0 * 8, (size_t)n_rays * row, sl.dev_out, (size_t)cnt * row,
+                                      (size_t)cnt * row, (size_t)slabs, cudaMemcpyDeviceToHost, sl.stream);
+            } else {
+                for (int j = 0; j < slabs && e == cudaSuccess; j++)
+                    e = cudaMemcpyAsync(out_host + ((size_t)j * n_rays + r0) * 8, sl.dev_out + (size_t)j * cnt * 8,
+                                        (size_t)cnt * row, cudaMemcpyDeviceToHost, sl.stream);
+            }
+            if ((rc = cuda_failed(e, "copy-out"))) return rc;
+        }
+        if ((rc = cuda_failed(cudaEventRecord(sl.done, sl.stream), "cudaEventRecord"))) return rc;
+        pending[s].active = true;
+        pending[s].r0 = r0;
+        pending[s].cnt = cnt;
+        return RTB_OK;
     };
     auto run_pipeline = [&]() -> int {
         // (equal chunks: ones that taper towards both ends of the call -- to shrink the copy-in and copy-out that have
@@ -911,11 +941,10 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
                 memcpy(sl.pin_in, src, (size_t)cnt * row);
                 src = sl.pin_in;
             }
-            mark(sl.stream);
             if ((rc = cuda_failed(cudaMemcpyAsync(sl.dev_in, src, (size_t)cnt * row, cudaMemcpyHostToDevice, sl.stream),
                                   "copy-in")))
                 return rc;
-            mark(sl.stream);
+            if (lag && (rc = cuda_failed(cudaEventRecord(sl.copied_in, sl.stream), "cudaEventRecord"))) return rc;
             P.rays_in = sl.dev_in;
             P.out = sl.dev_out;
             P.n_rays = cnt;
@@ -923,28 +952,16 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
             if (c == g_host_fail_chunk.load(std::memory_order_relaxed))
                 return fail(RTB_ERR_CUDA, "injected failure before the launch of chunk %lld (rtb_tune host_fail_chunk)", c);
             if ((rc = launch(P, opts->precision, ctx, device, sl.stream, sl.lean_counts))) return rc;
-            mark(sl.stream);
-            if (slabs > 0) {
-                cudaError_t e = cudaSuccess;
-                if (!out_pinned) {
-                    e = cudaMemcpyAsync(sl.pin_out, sl.dev_out, (size_t)cnt * row * slabs, cudaMemcpyDeviceToHost, sl.stream);
-                } else if (strided_copy_ok) {
-                    // (slabs, cnt, 8) device -> rows [r0, r0+cnt) of every slab of the (slabs, N, 8) host array
-                    e = cudaMemcpy2DAsync(out_host + (size_t)r0 * 8, (size_t)n_rays * row, sl.dev_out, (size_t)cnt * row,
-                                          (size_t)cnt * row, (size_t)slabs, cudaMemcpyDeviceToHost, sl.stream);
-                } else {
-                    for (int j = 0; j < slabs && e == cudaSuccess; j++)
-                        e = cudaMemcpyAsync(out_host + ((size_t)j * n_rays + r0) * 8, sl.dev_out + (size_t)j * cnt * 8,
-                                            (size_t)cnt * row, cudaMemcpyDeviceToHost, sl.stream);
-                }
-                if ((rc = cuda_failed(e, "copy-out"))) return rc;
+            if (!lag) {
+                if ((rc = copy_out(c))) return rc;
+            } else if (c > 0) {
+                if ((rc = cuda_failed(cudaStreamWaitEvent(ctx->slot[(c - 1) % kSlots].stream, sl.copied_in, 0),
+                                      "cudaStreamWaitEvent")))
+                    return rc;
+                if ((rc = copy_out(c - 1))) return rc;
             }
-            mark(sl.stream);
-            if ((rc = cuda_failed(cudaEventRecord(sl.done, sl.stream), "cudaEventRecord"))) return rc;
-            pending[s].active = true;
-            pending[s].r0 = r0;
-            pending[s].cnt = cnt;
         }
+        if (lag && n_chunks > 0 && (rc = copy_out(n_chunks - 1))) return rc;
         // drain in issue order
         for (long long c = n_chunks; c < n_chunks + kSlots; c++)
             if ((rc = retire((int)(c % kSlots)))) return rc;
@@ -952,20 +969,6 @@ int rtb_trace_host(const rtb_system *sys, const double *rays_in_host, int64_t n_
     };
     rc = run_pipeline();
     if (rc) drain();
-    if (timeline && !marks.empty()) {
-        drain();
-        for (size_t k = 0; k + 3 < marks.size(); k += 4) {
-            float a = 0, b = 0, c = 0, d = 0;
-            cudaEventElapsedTime(&a, marks[0], marks[k]);
-            cudaEventElapsedTime(&b, marks[0], marks[k + 1]);
-            cudaEventElapsedTime(&c, marks[0], marks[k + 2]);
-            cudaEventElapsedTime(&d, marks[0], marks[k + 3]);
-            fprintf(stderr, "[rtb] chunk %3zu: copy-in %8.3f - %8.3f ms, kernels done %8.3f, copy-out done %8.3f\n", k / 4, a, b,
-                    c, d);
-        }
-        for (cudaEvent_t ev : marks) cudaEventDestroy(ev);
-        cudaGetLastError();
-    }
     return rc;
 }
 

@@ -15,6 +15,7 @@ int main(int argc, char **argv)
     const int use_kernel = argc > 3 ? atoi(argv[3]) : 1;  // 0: no kernel between the copies
     const int gate = argc > 4 ? atoi(argv[4]) : 1;        // 0: enqueue everything up front (stream order alone protects the buffers)
     const int verbose = argc > 5 ? atoi(argv[5]) : 0;
+    const int lag = argc > 6 ? atoi(argv[6]) : 0;         // 1: the copy-out of chunk c is issued behind the copy-in of chunk c + 1
     char *h_in, *h_out;
     CK(cudaHostAlloc(&h_in, total, cudaHostAllocDefault));
     CK(cudaHostAlloc(&h_out, total, cudaHostAllocDefault));
@@ -42,23 +43,38 @@ int main(int argc, char **argv)
         CK(cudaDeviceSynchronize());
         cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
         CK(cudaEventRecord(t0, st[0]));
+        std::vector<cudaEvent_t> hdone(k);
+        for (int s = 0; s < k; s++) CK(cudaEventCreateWithFlags(&hdone[s], cudaEventDisableTiming));
         for (size_t c = 0; c < n_chunks; c++) {
             const int s = (int)(c % k);
             if (gate && active[s]) CK(cudaEventSynchronize(done[s]));
             if (verbose && rep == 2) mark(st[s]);
             CK(cudaMemcpyAsync(d[s], h_in + c * chunk, chunk, cudaMemcpyHostToDevice, st[s]));
             if (verbose && rep == 2) mark(st[s]);
+            if (lag) CK(cudaEventRecord(hdone[s], st[s]));
             if (use_kernel) touch<<<(unsigned)((chunk / 8 + 255) / 256), 256, 0, st[s]>>>((double *)d[s], chunk / 8);
             if (verbose && rep == 2) mark(st[s]);
-            CK(cudaMemcpyAsync(h_out + c * chunk, d[s], chunk, cudaMemcpyDeviceToHost, st[s]));
-            if (verbose && rep == 2) mark(st[s]);
-            CK(cudaEventRecord(done[s], st[s]));
-            active[s] = true;
+            if (!lag) {
+                CK(cudaMemcpyAsync(h_out + c * chunk, d[s], chunk, cudaMemcpyDeviceToHost, st[s]));
+                if (verbose && rep == 2) mark(st[s]);
+                CK(cudaEventRecord(done[s], st[s]));
+                active[s] = true;
+            } else if (c > 0) {
+                const int p = (int)((c - 1) % k);
+                CK(cudaStreamWaitEvent(st[p], hdone[s], 0));
+                CK(cudaMemcpyAsync(h_out + (c - 1) * chunk, d[p], chunk, cudaMemcpyDeviceToHost, st[p]));
+                CK(cudaEventRecord(done[p], st[p]));
+                active[p] = true;
+            }
+        }
+        if (lag) {
+            const int p = (int)((n_chunks - 1) % k);
+            CK(cudaMemcpyAsync(h_out + (n_chunks - 1) * chunk, d[p], chunk, cudaMemcpyDeviceToHost, st[p]));
         }
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(t1, st[0])); CK(cudaEventSynchronize(t1));
         CK(cudaEventElapsedTime(&ms, t0, t1));
-        printf("pipeline chunk %zu MiB, %d streams, kernel %d, gate %d: %.2f ms, %.1f GB/s\n", chunk >> 20, k, use_kernel, gate, ms, 2.0 * total / ms / 1e6);
+        printf("pipeline chunk %zu MiB, %d streams, kernel %d, gate %d, lag %d: %.2f ms, %.1f GB/s\n", chunk >> 20, k, use_kernel, gate, lag, ms, 2.0 * total / ms / 1e6);
         for (size_t q = 0; q + 3 < marks.size() && q < 4 * 12; q += 4) {
             float x[4];
             for (int j = 0; j < 4; j++) cudaEventElapsedTime(&x[j], marks[0], marks[q + j]);
