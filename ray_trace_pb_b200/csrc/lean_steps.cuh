@@ -310,14 +310,16 @@ __device__ __forceinline__ bool lens_any(bool &ok, const DevSurface &s, double f
     // transverse unit vector of the direction (raytrace.py:1704-1715)
     const double rnd = dot3_np(r.dx, r.dy, r.dz, s.nx, s.ny, s.nz);
     double px = r.dx - rnd * s.nx, py = r.dy - rnd * s.ny, pz = r.dz - rnd * s.nz;
-    const double pn = sqrt_chk(ok, sumsq3(px, py, pz));
+    // (a vector over its own norm, like d x n at a sphere: with 2^-969 <= |v|^2 < 2^104 and numerators that pass num_ok
+    // the quotients are normal numbers -- no range test per quotient)
+    const double pn = sqrt_unit_chk(ok, sumsq3(px, py, pz));
     ok &= pn > kPerpTol;                                                            // else: left un-normalised (careful path)
-    div3_zero_z(ok, px, py, pz, pn);
+    unit3_zero_z(ok, px, py, pz, pn);
     // height vector in the front focal plane (raytrace.py:1720-1728)
     const double hx = ax - fx, hy = ay - fy, hz = az - fz;
-    const double hn = sqrt_chk(ok, sumsq3(hx, hy, hz));
+    const double hn = sqrt_unit_chk(ok, sumsq3(hx, hy, hz));
     double ux = hx, uy = hy, uz = hz;
-    div3_zero_z(ok, ux, uy, uz, hn);
+    unit3_zero_z(ok, ux, uy, uz, hn);
     const double sin_t1 = dot3_np(px, py, pz, r.dx, r.dy, r.dz);                   // raytrace.py:1731
     // the ray in the back focal plane (raytrace.py:1736-1752)
     const double scale = (n1 * s.focal_len) * sin_t1;
