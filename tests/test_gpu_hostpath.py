@@ -130,3 +130,35 @@ def test_scalar_answering_material_and_bad_out(rt, rtm, oracle, dev):
             dev.trace_source(system.surfaces, mats, src, keep="last", out=bad)
         with pytest.raises(ValueError):
             dev.trace_sources(system.surfaces, mats, [src], keep="last", out=bad)
+
+
+@pytest.mark.parametrize("n_rays", [1, 262144, 262145, 3 * 262144 + 17, 5 * 262144 - 1])
+def test_lagged_pipeline_at_the_chunk_boundaries(n_rays, rt, rtm, oracle):
+    """rtb_trace_host issues the copy-out of chunk c behind the copy-in of chunk c + 1 (four slots, 262 144-ray chunks
+    for single-slab calls): one chunk, exactly one chunk, one ray more, a ragged tail, more chunks than slots --
+    pageable and pinned buffers, keep='last' and a keep list, every row against the oracle"""
+    from ray_trace_pb_b200 import _ffi, engine
+    system = systems.relay10_system(rt, rtm)
+    vac = rtm.Vacuum()
+    materials = [vac] + list(system.materials) + [vac]
+    rng = np.random.default_rng(n_rays)
+    rays = np.zeros((n_rays, 8))
+    rays[:, 0:2] = rng.uniform(-13.0, 13.0, (n_rays, 2))
+    d = rng.standard_normal((n_rays, 3)) * np.array([0.02, 0.02, 0.0]) + np.array([0.0, 0.0, 1.0])
+    rays[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 7] = 0.785
+    want = oracle.ray_trace(system, rays, vac, vac, n_threads=8)
+    # pageable in, result array from the library (pinned pool for big ones)
+    last = system.ray_trace(rays, vac, vac, keep="last")
+    parity.assert_bit_identical(last[0], want[-1], "pageable in, keep='last'")
+    # pageable in AND out
+    out = np.empty((1, n_rays, 8))
+    engine.trace_host(system.surfaces, materials, rays, keep="last", out=out)
+    parity.assert_bit_identical(out[0], want[-1], "pageable in and out")
+    # pinned in and out, keep list (strided copy-out)
+    pin_in = _ffi.pinned_empty(rays.shape)
+    pin_in[:] = rays
+    pin_out = _ffi.pinned_empty((3, n_rays, 8))
+    pin_out[:] = -1.0
+    engine.trace_host(system.surfaces, materials, pin_in, keep=[1, 12, 20], out=pin_out)
+    parity.assert_bit_identical(pin_out, want[[1, 12, 20]], "pinned, keep list")
