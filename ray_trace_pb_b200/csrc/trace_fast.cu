@@ -191,7 +191,9 @@ __device__ __forceinline__ bool lens_step(const DevSurface &s, const RayT<T> &in
 }
 
 // SWEEP (FROM_SOURCE only): blockIdx.y picks the source, its output rows and its reduction bucket (rtb_trace_sources)
-template <typename T, bool USE_TABLE, bool FROM_SOURCE, bool SWEEP = false>
+// LAST: the launch keeps nothing but the final slab and reduces nothing (the common fast-mode call): no per-surface slab
+// bookkeeping, a dead ray leaves the surface loop.
+template <typename T, bool USE_TABLE, bool FROM_SOURCE, bool SWEEP = false, bool LAST = false>
 __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel(const __grid_constant__ TraceParams P)
 {
     static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
@@ -223,8 +225,8 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
     const DevSource &source = sweep_source(P, s_sweep);
     const DevReduce &red = sweep_reduce(P, s_sweep);
     const long long row0 = SWEEP ? (long long)blockIdx.y * P.n_rays : 0;
-    const bool reducing = P.red.slab >= 0;
-    const bool intersect_only = (P.flags & RTB_FLAG_INTERSECT_ONLY) != 0;
+    const bool reducing = !LAST && P.red.slab >= 0;
+    const bool intersect_only = !LAST && (P.flags & RTB_FLAG_INTERSECT_ONLY) != 0;
     Tally tally;
     tally_init(tally);
 
@@ -237,7 +239,8 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
             first = make_ray(source, source.first + i);
         else
             load_ray(P.rays_in, i, P.n_rays, planes_in, first);
-        if (P.slab_pos[0] >= 0) store_ray(P.out + P.slab_pos[0] * P.out_stride, row0 + i, out_rows, planes_out, first);
+        if (!LAST && P.slab_pos[0] >= 0)
+            store_ray(P.out + P.slab_pos[0] * P.out_stride, row0 + i, out_rows, planes_out, first);
         if (reducing && P.red.slab == 0) reduce_sample(red, first, tally);
 
         // the ray, in registers: position / phase fp64, direction fp32; the wavelength only ever turns NaN with the
@@ -264,7 +267,8 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
             const DevSurface &s = P.surf[q];
             const double n2 = !USE_TABLE ? eval_index(P.mat[q + 1], wl0)
                                          : (unlisted ? index_for_unlisted(&P.mat[q + 1], wl0) : s_ntab[row + q + 1]);
-            const int act = P.slab_act[q];
+            if (LAST && dead) break;
+            const int act = LAST ? 0 : P.slab_act[q];
             auto emit = [&](bool at_slab, const Ray &w) {
                 const int pos = P.slab_pos[2 * q + (at_slab ? 1 : 2)];
                 if (act & (at_slab ? 1 : 2)) store_ray(P.out + pos * P.out_stride, row0 + i, out_rows, planes_out, w);
@@ -358,11 +362,19 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
             }
             n1 = n2;
         }
+        if (LAST) {
+            // the final slab's row (slab_pos[2 S] = 0): the ray as it left the last surface, blank when it died
+            Ray w;
+            w.ox = ox; w.oy = oy; w.oz = oz; w.dx = (double)dx; w.dy = (double)dy; w.dz = (double)dz; w.ph = ph;
+            w.wl = wl0;
+            if (dead) set_nan(w);
+            store_ray(P.out, row0 + i, out_rows, planes_out, w);
+        }
     }
     if (reducing) tally_flush(red, tally);
 }
 
-template <typename T>
+template <typename T, bool LAST>
 cudaError_t launch_fast(const TraceParams &P, unsigned b, int threads, cudaStream_t stream)
 {
     const bool table = P.n_wl > 0;
@@ -370,19 +382,19 @@ cudaError_t launch_fast(const TraceParams &P, unsigned b, int threads, cudaStrea
     if (P.n_src > 0) {
         const dim3 grid(b, (unsigned)P.n_src);
         if (table)
-            trace_fast_kernel<T, true, true, true><<<grid, threads, 0, stream>>>(P);
+            trace_fast_kernel<T, true, true, true, LAST><<<grid, threads, 0, stream>>>(P);
         else
-            trace_fast_kernel<T, false, true, true><<<grid, threads, 0, stream>>>(P);
+            trace_fast_kernel<T, false, true, true, LAST><<<grid, threads, 0, stream>>>(P);
         return cudaGetLastError();
     }
     if (table && source)
-        trace_fast_kernel<T, true, true><<<b, threads, 0, stream>>>(P);
+        trace_fast_kernel<T, true, true, false, LAST><<<b, threads, 0, stream>>>(P);
     else if (table)
-        trace_fast_kernel<T, true, false><<<b, threads, 0, stream>>>(P);
+        trace_fast_kernel<T, true, false, false, LAST><<<b, threads, 0, stream>>>(P);
     else if (source)
-        trace_fast_kernel<T, false, true><<<b, threads, 0, stream>>>(P);
+        trace_fast_kernel<T, false, true, false, LAST><<<b, threads, 0, stream>>>(P);
     else
-        trace_fast_kernel<T, false, false><<<b, threads, 0, stream>>>(P);
+        trace_fast_kernel<T, false, false, false, LAST><<<b, threads, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -396,8 +408,13 @@ cudaError_t launch_trace_fast(const TraceParams &P, int precision, int sm_count,
     long long max_blocks = (long long)sm_count * 32;
     if (P.n_src > 0) max_blocks = (max_blocks + P.n_src - 1) / P.n_src;   // the cap is for the whole grid
     if (blocks > max_blocks) blocks = max_blocks;
-    return precision == RTB_F64_FAST ? launch_fast<double>(P, (unsigned)blocks, threads, stream)
-                                     : launch_fast<float>(P, (unsigned)blocks, threads, stream);
+    // nothing but the final slab, no reduction: the instantiations without per-surface slab bookkeeping
+    const bool last = P.store_last_only && P.red.slab < 0 && (P.flags & RTB_FLAG_INTERSECT_ONLY) == 0 && P.n_surf > 0;
+    if (precision == RTB_F64_FAST)
+        return last ? launch_fast<double, true>(P, (unsigned)blocks, threads, stream)
+                    : launch_fast<double, false>(P, (unsigned)blocks, threads, stream);
+    return last ? launch_fast<float, true>(P, (unsigned)blocks, threads, stream)
+                : launch_fast<float, false>(P, (unsigned)blocks, threads, stream);
 }
 
 } // namespace rtb

@@ -849,6 +849,10 @@ def test_fast_modes_tolerance(name, precision, rt, rtm):
     ph_ok = ok[..., 6]
     assert (err[..., 6][ph_ok] <= tol_ph * np.maximum(scale[..., 6][ph_ok], 1.0)).all()
     assert np.array_equal(got[..., 7][ok[..., 7]], want[..., 7][ok[..., 7]])
+    # the final-slab-only instantiations of the fast kernels (no per-surface slab bookkeeping, dead rays leave the loop)
+    # perform the same arithmetic: same bits as the last slab of the full history
+    last = system.ray_trace(g["rays_in"], m_in, m_out, precision=precision, keep="last")
+    parity.assert_bit_identical(last[0], got[-1], f"{name} {precision}: keep='last' vs the history's last slab")
 
 
 def test_exact_math_selftest():
