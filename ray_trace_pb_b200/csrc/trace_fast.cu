@@ -191,9 +191,10 @@ __device__ __forceinline__ bool lens_step(const DevSurface &s, const RayT<T> &in
 }
 
 // SWEEP (FROM_SOURCE only): blockIdx.y picks the source, its output rows and its reduction bucket (rtb_trace_sources)
-// LAST: the launch keeps nothing but the final slab and reduces nothing (the common fast-mode call): no per-surface slab
-// bookkeeping, a dead ray leaves the surface loop.
-template <typename T, bool USE_TABLE, bool FROM_SOURCE, bool SWEEP = false, bool LAST = false>
+// LAST = 1: the launch keeps nothing but the final slab and reduces nothing (the common fast-mode call): no per-surface
+// slab bookkeeping, a dead ray leaves the surface loop.  LAST = 2: the final slab or nothing, plus the fused reduction
+// at one slab behind the launch rays (the analysis launches: spot statistics, pupil grids) -- no slab stores in the loop.
+template <typename T, bool USE_TABLE, bool FROM_SOURCE, bool SWEEP = false, int LAST = 0>
 __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel(const __grid_constant__ TraceParams P)
 {
     static_assert(!SWEEP || FROM_SOURCE, "sweeps generate their rays");
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
     const DevSource &source = sweep_source(P, s_sweep);
     const DevReduce &red = sweep_reduce(P, s_sweep);
     const long long row0 = SWEEP ? (long long)blockIdx.y * P.n_rays : 0;
-    const bool reducing = !LAST && P.red.slab >= 0;
+    const bool reducing = LAST != 1 && P.red.slab >= 0;
     const bool intersect_only = !LAST && (P.flags & RTB_FLAG_INTERSECT_ONLY) != 0;
     Tally tally;
     tally_init(tally);
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
             const double n2 = !USE_TABLE ? eval_index(P.mat[q + 1], wl0)
                                          : (unlisted ? index_for_unlisted(&P.mat[q + 1], wl0) : s_ntab[row + q + 1]);
             if (LAST && dead) break;
-            const int act = LAST ? 0 : P.slab_act[q];
+            const int act = LAST == 1 ? 0 : (LAST == 2 ? (P.slab_act[q] & 12) : P.slab_act[q]);
             auto emit = [&](bool at_slab, const Ray &w) {
                 const int pos = P.slab_pos[2 * q + (at_slab ? 1 : 2)];
                 if (act & (at_slab ? 1 : 2)) store_ray(P.out + pos * P.out_stride, row0 + i, out_rows, planes_out, w);
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
             }
             n1 = n2;
         }
-        if (LAST) {
+        if (LAST && P.any_store) {
             // the final slab's row (slab_pos[2 S] = 0): the ray as it left the last surface, blank when it died
             Ray w;
             w.ox = ox; w.oy = oy; w.oz = oz; w.dx = (double)dx; w.dy = (double)dy; w.dz = (double)dz; w.ph = ph;
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6) trace_fast_kernel
     if (reducing) tally_flush(red, tally);
 }
 
-template <typename T, bool LAST>
+template <typename T, int LAST>
 cudaError_t launch_fast(const TraceParams &P, unsigned b, int threads, cudaStream_t stream)
 {
     const bool table = P.n_wl > 0;
@@ -408,13 +409,19 @@ cudaError_t launch_trace_fast(const TraceParams &P, int precision, int sm_count,
     long long max_blocks = (long long)sm_count * 32;
     if (P.n_src > 0) max_blocks = (max_blocks + P.n_src - 1) / P.n_src;   // the cap is for the whole grid
     if (blocks > max_blocks) blocks = max_blocks;
-    // nothing but the final slab, no reduction: the instantiations without per-surface slab bookkeeping
-    const bool last = P.store_last_only && P.red.slab < 0 && (P.flags & RTB_FLAG_INTERSECT_ONLY) == 0 && P.n_surf > 0;
+    // nothing but the final slab (or nothing at all) and at most one reduction behind the launch rays: the
+    // instantiations without per-surface slab bookkeeping
+    const bool plain = (P.flags & RTB_FLAG_INTERSECT_ONLY) == 0 && P.n_surf > 0;
+    const int last = !plain ? 0
+                     : (P.store_last_only && P.red.slab < 0) ? 1
+                     : ((P.store_last_only || !P.any_store) && P.red.slab >= 1) ? 2 : 0;
     if (precision == RTB_F64_FAST)
-        return last ? launch_fast<double, true>(P, (unsigned)blocks, threads, stream)
-                    : launch_fast<double, false>(P, (unsigned)blocks, threads, stream);
-    return last ? launch_fast<float, true>(P, (unsigned)blocks, threads, stream)
-                : launch_fast<float, false>(P, (unsigned)blocks, threads, stream);
+        return last == 1 ? launch_fast<double, 1>(P, (unsigned)blocks, threads, stream)
+               : last == 2 ? launch_fast<double, 2>(P, (unsigned)blocks, threads, stream)
+                           : launch_fast<double, 0>(P, (unsigned)blocks, threads, stream);
+    return last == 1 ? launch_fast<float, 1>(P, (unsigned)blocks, threads, stream)
+           : last == 2 ? launch_fast<float, 2>(P, (unsigned)blocks, threads, stream)
+                       : launch_fast<float, 0>(P, (unsigned)blocks, threads, stream);
 }
 
 } // namespace rtb

@@ -474,6 +474,19 @@ def test_sweep_in_one_launch_equals_per_source_launches(rt, rtm, oracle, dev, to
             np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-9)
             np.testing.assert_allclose(red.grid[k].cpu().numpy(), one.grid.cpu().numpy(), rtol=0, atol=1e-9)
             assert red.grid[k][2].sum().item() == one.grid[2].sum().item()
+        # the same sweep keeping only the final slab / nothing: other kernel instantiations (the fast modes' final-slab
+        # + reduction kernels, the exact mode's lean kernels), the same rows and the same reductions
+        for keep in ("last", "none"):
+            red2 = dev.Reducer(slab, origin=(8.0, 0, 0), grid_n=64, half_width=8.0, buckets=len(sources))
+            out2 = dev.trace_sources(system.surfaces, mats, sources, keep=keep, precision=precision, reducer=red2)
+            if keep == "last":
+                parity.assert_bit_identical(out2[0].cpu().numpy(), out[2].cpu().numpy(), f"final slab, keep='last' ({precision})")
+            a, b = red2.stats_t.cpu().numpy(), red.stats_t.cpu().numpy()
+            assert (a[:, 0] == b[:, 0]).all()
+            np.testing.assert_array_equal(a[:, 8:], b[:, 8:])
+            np.testing.assert_allclose(a[:, 1:8], b[:, 1:8], rtol=1e-11, atol=1e-9)
+            np.testing.assert_array_equal(red2.grid[:, 2].cpu().numpy(), red.grid[:, 2].cpu().numpy())
+            np.testing.assert_allclose(red2.grid.cpu().numpy(), red.grid.cpu().numpy(), rtol=0, atol=1e-9)
         if precision == "f64":       # and against the oracle on the generated rays
             rays = out[0].cpu().numpy()
             want = oracle.ray_trace(system, rays, vac, vac, n_threads=8)
