@@ -245,6 +245,9 @@ int64_t rtb_pure_launch_count(void);
  *                    synchronises.  0: the probe-driven kernels always.  2: the pure kernels whatever the bundle (tests).
  *                    RTB_LEAN_PURE sets the initial value.  A stale verdict costs time only: failing rays are re-traced.
  *                    Setting the mode forgets every cached verdict.
+ *   "sweep_split_rays" rtb_trace_sources traces sweeps of at least this many rays per source (default 2^24) as one launch
+ *                    per source -- source and reduction bucket in the kernel parameters -- instead of one launch for all;
+ *                    negative = never.  RTB_SWEEP_SPLIT_RAYS sets the initial value.  Same rows, same buckets.
  *   "keep_probe_counts" test hook: 1 = every lean launch synchronises and keeps its probe's per-surface counts for
  *                    rtb_last_probe_counts().
  *   "host_fail_chunk" test hook: rtb_trace_host returns RTB_ERR_CUDA when it is about to launch chunk n (0-based) of a

@@ -59,6 +59,12 @@ unsigned g_last_probe_counts[2 * RTB_MAX_SURFACES];
 // 2 = the pure kernels whenever the system has a lean step for every surface, whatever the bundle (tests).
 std::atomic<long long> g_lean_pure{1};
 std::atomic<long long> g_pure_launches{0};
+// rtb_trace_sources traces sweeps of at least this many rays per source as one launch PER SOURCE (each with its source and
+// its reduction bucket in the kernel parameters, i.e. warp-uniform operands) instead of one launch whose blocks fetch
+// theirs from shared memory.  Measured: 3 x 16.8 M rays +3.6 % (BASELINE config 2: 65.3 -> 67.7 G ray*surf/s), but
+// 32 x 4.2 M rays -5.7 % (config 3: each launch pays its own probe and its own tail), so only really big sources are
+// split.  rtb_tune("sweep_split_rays", n); RTB_SWEEP_SPLIT_RAYS; negative = never.
+std::atomic<long long> g_sweep_split_rays{1 << 24};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -115,7 +121,7 @@ struct Slot {
 // costs time, never a bit of the result: rays that fail a lean step are re-traced by redo_ray in every kernel.  A key
 // whose verdict keeps changing (one system traced alternately with bundles of different character from device arrays)
 // stays with the probe-driven kernels.
-constexpr int kVerdictEntries = 16;
+constexpr int kVerdictEntries = 128;
 constexpr int kVerdictMaxSources = 64;
 
 struct VerdictEntry {
@@ -124,7 +130,8 @@ struct VerdictEntry {
     unsigned long long general = 0;   // the last consumed probe's verdict (lean_verdict_from_counts)
     int flips = 0, stable = 0;
     int pending_n_src = 0, pending_n_surf = 0;
-    unsigned *pin = nullptr;          // kVerdictMaxSources x kMaxSurfaces x 2 counts, page-locked
+    unsigned *pin = nullptr;          // pin_sources x kMaxSurfaces x 2 counts, page-locked
+    int pin_sources = 0;
     cudaEvent_t ev = nullptr;
     unsigned long long stamp = 0;
 };
@@ -435,6 +442,7 @@ bool wants_lean(const rtb::TraceParams &P, int precision)
         if (const char *env = getenv("RTB_LEAN_MIN_RAYS")) g_lean_min_rays.store(atoll(env), std::memory_order_relaxed);
         if (const char *env = getenv("RTB_LEAN_MIN_SHARE_PCT")) rtb::set_lean_min_share_pct(atoi(env));
         if (const char *env = getenv("RTB_LEAN_PURE")) g_lean_pure.store(std::min(2ll, std::max(0ll, atoll(env))), std::memory_order_relaxed);
+        if (const char *env = getenv("RTB_SWEEP_SPLIT_RAYS")) g_sweep_split_rays.store(atoll(env), std::memory_order_relaxed);
         return true;
     }();
     (void)env_read;
@@ -505,17 +513,25 @@ VerdictEntry *verdict_lookup(DeviceCtx *ctx, unsigned long long key, int n_src, 
         if (!victim) return nullptr;
         e = victim;
         unsigned *pin = e->pin;
+        const int pin_sources = e->pin_sources;
         cudaEvent_t ev = e->ev;
         *e = VerdictEntry();
         e->pin = pin;
+        e->pin_sources = pin_sources;
         e->ev = ev;
         e->used = true;
         e->key = key;
-        if (!e->pin && cudaHostAlloc((void **)&e->pin, sizeof(unsigned) * 2 * rtb::kMaxSurfaces * kVerdictMaxSources,
-                                     cudaHostAllocDefault) != cudaSuccess) {
-            cudaGetLastError();
-            e->used = false;
-            return nullptr;
+        if (e->pin_sources < n_src) {
+            if (e->pin) cudaFreeHost(e->pin);
+            e->pin = nullptr;
+            e->pin_sources = 0;
+            if (cudaHostAlloc((void **)&e->pin, sizeof(unsigned) * 2 * rtb::kMaxSurfaces * (size_t)n_src,
+                              cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                e->used = false;
+                return nullptr;
+            }
+            e->pin_sources = n_src;
         }
         if (!e->ev && cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
@@ -739,6 +755,10 @@ int rtb_tune(const char *key, int64_t value)
         }
         return RTB_OK;
     }
+    if (strcmp(key, "sweep_split_rays") == 0) {
+        g_sweep_split_rays.store(value, std::memory_order_relaxed);
+        return RTB_OK;
+    }
     if (strcmp(key, "keep_probe_counts") == 0) {
         g_keep_probe_counts.store(value, std::memory_order_relaxed);
         return RTB_OK;
@@ -810,6 +830,29 @@ int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_s
     DeviceGuard guard;
     if ((rc = guard.enter(device))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        wants_lean(P, opts->precision);          // (reads the environment once)
+        const long long split = g_sweep_split_rays.load(std::memory_order_relaxed);
+        if (n_src > 1 && split >= 0 && n_rays_each >= split) {
+            // one launch per source: rows [k n, (k + 1) n) of every kept slab, bucket k of the reductions
+            const bool planes_out = (opts->flags & RTB_FLAG_PLANES_OUT) != 0;
+            for (int k = 0; k < n_src; k++) {
+                rtb::TraceParams Q = P;
+                Q.src = list[(size_t)k];
+                Q.src_list = nullptr;
+                Q.n_src = 0;
+                Q.rays_in = nullptr;
+                Q.out = out_dev ? out_dev + (size_t)k * (size_t)n_rays_each * (planes_out ? 1 : 8) : nullptr;
+                Q.n_rays = n_rays_each;
+                Q.out_stride = 8 * (long long)n_rays_each * n_src;
+                if (Q.red.stats) Q.red.stats += (long long)k * RTB_N_STATS;
+                if (Q.red.grid) Q.red.grid += (long long)k * 3 * Q.red.grid_n * Q.red.grid_n;
+                rtb::finish_reduce(Q.red);
+                if ((rc = launch(Q, opts->precision, ctx, device, st, nullptr, source_key(&list[(size_t)k], 1)))) return rc;
+            }
+            return RTB_OK;
+        }
+    }
     // the list lives in stream-ordered device memory for exactly this launch (pageable source: the copy has staged
     // it by the time the call returns, so the vector may go out of scope)
     rtb::DevSource *list_dev = nullptr;

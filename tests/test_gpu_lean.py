@@ -197,7 +197,16 @@ def test_lean_equals_general_kernels_with_reductions(rt, rtm, oracle, dev, torch
         np.testing.assert_allclose(g1[:2], wg[:2], rtol=0, atol=1e-9 * max(1.0, np.abs(wg[2]).max()))
 
 
-def test_lean_sweep_equals_per_source_launches(rt, rtm, dev, torch, lean):
+@pytest.fixture(params=["one_launch", "launch_per_source"])
+def sweep_form(request):
+    from ray_trace_pb_b200 import _ffi
+    L = _ffi.lib()
+    _ffi.check(L.rtb_tune(b"sweep_split_rays", 0 if request.param == "launch_per_source" else -1))
+    yield request.param
+    _ffi.check(L.rtb_tune(b"sweep_split_rays", 1 << 24))
+
+
+def test_lean_sweep_equals_per_source_launches(rt, rtm, dev, torch, lean, sweep_form):
     """rtb_trace_sources (grid y = source, per-source probe counts and reduction buckets) through the lean kernel"""
     system = systems.relay10_system(rt, rtm)
     vac = rtm.Vacuum()

@@ -448,7 +448,18 @@ def test_sources_generate_and_fused_trace(kind, rt, rtm, oracle, dev):
 
 
 # ------------------------------------------------------------------------------------------------ reductions
-def test_sweep_in_one_launch_equals_per_source_launches(rt, rtm, oracle, dev, torch):
+@pytest.fixture(params=["one_launch", "launch_per_source"])
+def sweep_form(request):
+    """rtb_trace_sources' two forms: one launch whose grid y is the source (small sources), one launch per source with
+    its source and bucket in the kernel parameters (rtb_tune "sweep_split_rays": sources of 2^24 rays and more)"""
+    from ray_trace_pb_b200 import _ffi
+    L = _ffi.lib()
+    _ffi.check(L.rtb_tune(b"sweep_split_rays", 0 if request.param == "launch_per_source" else -1))
+    yield request.param
+    _ffi.check(L.rtb_tune(b"sweep_split_rays", 1 << 24))
+
+
+def test_sweep_in_one_launch_equals_per_source_launches(rt, rtm, oracle, dev, torch, sweep_form):
     """rtb_trace_sources: field x wavelength sweep, grid y = source; rows, statistics and grids per source"""
     system = systems.relay10_system(rt, rtm)
     vac = rtm.Vacuum()
