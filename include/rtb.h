@@ -242,7 +242,8 @@ int64_t rtb_pure_launch_count(void);
  *                    through the uniform datapath, +4 % -- once the probe of an EARLIER launch of the same system (and,
  *                    for on-device sources, the same source description) has found no surface where whole bundles fail
  *                    the lean step; every launch's probe counts are read back asynchronously for the next one, nothing
- *                    synchronises.  0: the probe-driven kernels always.  2: the pure kernels whatever the bundle (tests).
+ *                    synchronises (launches from on-device sources, whose rays the key determines, drop the probe once
+ *                    their verdict is in).  0: the probe-driven kernels always.  2: the pure kernels whatever the bundle (tests).
  *                    RTB_LEAN_PURE sets the initial value.  A stale verdict costs time only: failing rays are re-traced.
  *                    Setting the mode forgets every cached verdict.
  *   "sweep_split_rays" rtb_trace_sources traces sweeps of at least this many rays per source (default 2^24) as one launch

@@ -20,7 +20,8 @@ bool lean_eligible(const TraceParams &P);
 void set_lean_min_share_pct(int pct);
 void set_psf_dmma(int on);
 cudaError_t launch_trace_lean(const TraceParams &P, unsigned *counts, int sm_count, cudaStream_t stream, int *launches,
-                              int pure_mode, unsigned long long verdict_general, bool *pure_used);
+                              int pure_mode, unsigned long long verdict_general, bool *pure_used, bool probe_optional,
+                              bool *probed);
 unsigned long long lean_verdict_from_counts(const unsigned *counts, int n_src, int n_surf);
 cudaError_t launch_generate(const DevSource &src, long long n_rays, double *out, int sm_count, cudaStream_t stream);
 cudaError_t launch_reduce_init(const DevReduce &red, int sm_count, cudaStream_t stream);
@@ -480,15 +481,14 @@ unsigned long long verdict_key(const rtb::TraceParams &P, unsigned long long bun
     return h ? h : 1ull;
 }
 
-unsigned long long source_key(const rtb::DevSource *list, int n)
+// (the whole description, first ray and count included: the rays of such a launch are a pure function of the key, so a
+// verdict, once read back, is final -- launch() then drops the probe)
+unsigned long long source_key(const rtb::DevSource *list, int n, long long n_rays)
 {
     unsigned long long h = 0x84222325cbf29ce4ull;
-    for (int k = 0; k < n; k++) {
-        rtb::DevSource d = list[k];
-        d.first = 0;                      // (a shard of a source is the same kind of bundle)
-        h = hash_bytes(h, &d, sizeof(d));
-    }
-    return h;
+    h = hash_bytes(h, &n_rays, sizeof(n_rays));
+    for (int k = 0; k < n; k++) h = hash_bytes(h, &list[k], sizeof(list[k]));
+    return h ? h : 1ull;
 }
 
 // Consume a finished read-back, then say which kernel this launch should use.  Returns the entry that may take this
@@ -596,13 +596,17 @@ int launch(const rtb::TraceParams &P, int precision, DeviceCtx *ctx, int device,
                 entry = verdict_lookup(ctx, verdict_key(P, bundle_key), n_src, &pure_mode, &general);
             }
         }
-        bool pure_used = false;
-        cudaError_t e = rtb::launch_trace_lean(P, counts, ctx->sm_count, stream, &launches, pure_mode, general, &pure_used);
+        bool pure_used = false, probed = false;
+        // (on-device sources: the key determines the rays, the verdict that came back for it is final)
+        const bool final_verdict = bundle_key != 0ull && pure_mode == 1 &&
+                                   !g_keep_probe_counts.load(std::memory_order_relaxed);
+        cudaError_t e = rtb::launch_trace_lean(P, counts, ctx->sm_count, stream, &launches, pure_mode, general, &pure_used,
+                                               final_verdict, &probed);
         static const bool debug = getenv("RTB_LEAN_DEBUG") != nullptr;
         if (debug)
             fprintf(stderr, "[rtb] lean launch: %lld rays x %d src, mode %d, verdict %#llx, entry %p -> %s\n", (long long)P.n_rays,
                     n_src, pure_mode, general, (void *)entry, pure_used ? "pure" : "probe-driven");
-        if (e == cudaSuccess && entry) {
+        if (e == cudaSuccess && entry && probed) {
             // this launch's probe counts, for the next launch of the same key
             if (cudaMemcpyAsync(entry->pin, counts, bytes, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
                 cudaEventRecord(entry->ev, stream) == cudaSuccess) {
@@ -806,7 +810,7 @@ int rtb_trace_source(const rtb_system *sys, const rtb_source *src, int64_t first
     P.out = out_dev;
     P.n_rays = n_rays;
     P.out_stride = 8 * (long long)n_rays;
-    return launch(P, opts->precision, ctx, device, (cudaStream_t)stream, nullptr, source_key(&P.src, 1));
+    return launch(P, opts->precision, ctx, device, (cudaStream_t)stream, nullptr, source_key(&P.src, 1, P.n_rays));
 }
 
 int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_src, int64_t first_ray,
@@ -848,7 +852,7 @@ int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_s
                 if (Q.red.stats) Q.red.stats += (long long)k * RTB_N_STATS;
                 if (Q.red.grid) Q.red.grid += (long long)k * 3 * Q.red.grid_n * Q.red.grid_n;
                 rtb::finish_reduce(Q.red);
-                if ((rc = launch(Q, opts->precision, ctx, device, st, nullptr, source_key(&list[(size_t)k], 1)))) return rc;
+                if ((rc = launch(Q, opts->precision, ctx, device, st, nullptr, source_key(&list[(size_t)k], 1, n_rays_each)))) return rc;
             }
             return RTB_OK;
         }
@@ -872,7 +876,7 @@ int rtb_trace_sources(const rtb_system *sys, const rtb_source *srcs, int32_t n_s
     P.out = out_dev;
     P.n_rays = n_rays_each;
     P.out_stride = 8 * (long long)n_rays_each * n_src;
-    rc = launch(P, opts->precision, ctx, device, st, nullptr, source_key(list.data(), n_src));
+    rc = launch(P, opts->precision, ctx, device, st, nullptr, source_key(list.data(), n_src, n_rays_each));
     cudaFreeAsync(list_dev, st);
     return rc;
 }

@@ -777,11 +777,16 @@ bool build_runs(TraceParams &P, unsigned long long general)
 // surfaces at which an EARLIER probe of the same system and bundle found bundle-wide failures of the plain lean step
 // (rtb_api.cu's cache; on-axis flats among them run the zero-tolerant lean flat, anything else sends the launch back to the
 // probe-driven kernels).  2: the pure kernels with no verdict (tests: whatever fails is re-traced by redo_ray).  The probe
-// runs in every mode -- in the pure modes its counts only feed the caller's next verdict.  *pure_used says what ran.
+// runs in every mode but one (see probe_optional) -- in the pure modes its counts only feed the caller's next verdict.
+// *pure_used says what ran.
+// `probe_optional`: the verdict is final for this launch (rays that are a pure function of the cache key): when the pure
+// kernels take it, the probe -- which would only confirm it -- is not launched.  *probed says whether it was.
 cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_count, cudaStream_t stream, int *launches,
-                              int pure_mode, unsigned long long verdict_general, bool *pure_used)
+                              int pure_mode, unsigned long long verdict_general, bool *pure_used, bool probe_optional,
+                              bool *probed)
 {
     if (pure_used) *pure_used = false;
+    if (probed) *probed = false;
     if (P_in.n_rays <= 0) return cudaSuccess;
     TraceParams P = P_in;
     const bool sweep = P.n_src > 0;
@@ -798,6 +803,8 @@ cudaError_t launch_trace_lean(const TraceParams &P_in, unsigned *counts, int sm_
     else
         build_runs(P, P.lean_general);
     if (pure_used) *pure_used = P.lean_pure != 0;
+    if (P.lean_pure != 0 && probe_optional) counts = nullptr;
+    if (probed) *probed = counts != nullptr;
     cudaError_t e;
     P.lean_counts = nullptr;
     if (counts) {

@@ -323,15 +323,21 @@ def test_verdict_cache_sources_and_sweeps(rt, rtm, dev, torch, cache):
     thetas = np.linspace(0.001, np.pi / 180, 4)
     sources = [dev.RaySource.grid([0, 0, 0], 12.0, 151, 0.785, normal=(0.6 * np.sin(t), 0.8 * np.sin(t), np.cos(t)))
                for t in thetas]
-    outs, used = [], []
+    from ray_trace_pb_b200 import _ffi
+    L = _ffi.lib()
+    outs, used, kernels = [], [], []
     for _ in range(3):
-        before = cache()
         red = dev.Reducer(20, buckets=len(sources), grid_n=32, half_width=12.0)
+        torch.cuda.synchronize()
+        before, launched = cache(), L.rtb_launch_count()
         out = dev.trace_sources(system.surfaces, mats, sources, keep="last", reducer=red)
         torch.cuda.synchronize()
         used.append(cache() - before)
+        kernels.append(L.rtb_launch_count() - launched)
         outs.append((out.cpu().numpy(), red.stats_t.cpu().numpy(), red.grid.cpu().numpy()))
     assert used == [0, 1, 1], used
+    # the rays of an on-device source are a pure function of the key: once its verdict is in, the probe is not launched
+    assert kernels == [2, 1, 1], kernels
     for o, s, g in outs[1:]:
         parity.assert_bit_identical(o, outs[0][0], "sweep, pure vs probe-driven")
         assert (s[:, 0] == outs[0][1][:, 0]).all()
